@@ -1,0 +1,157 @@
+/*
+ * gsplat_b200.h -- C ABI of libgsplat_b200.so: the sm_100a (NVIDIA B200) implementation of the
+ * differentiable Gaussian-splat render path that sits behind OpenSplat's libtorch autograd
+ * operators ProjectGaussians / RasterizeGaussians / SphericalHarmonics.
+ *
+ * This is the drop-in boundary: every entry point replaces one `*_tensor` binding of the
+ * reference's CUDA back end (rasterizer/gsplat/bindings.h, cited per function as file:line under
+ * /root/reference) or one ATen call the reference operator makes between them
+ * (rasterize_gaussians.cpp:25-32,62-63).  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless said otherwise; fp32 / int32 / int64, dense row-major.
+ *  - The caller owns all memory (inputs, outputs, workspaces); the library never allocates or
+ *    frees device memory and keeps no mutable global state.  Workspace sizes come from the
+ *    `*_bytes` queries.  Outputs are fully written by the call (no pre-zeroing required) unless
+ *    noted.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*); no call
+ *    synchronises the device.  Entry points are re-entrant and thread-safe (distinct streams /
+ *    devices may be driven concurrently); the current CUDA device of the calling thread is used.
+ *  - Return value: 0 on success, otherwise a cudaError_t (>0) or GSB_ERR_* (<0).  A description of
+ *    the last error on the calling thread is available from gsb_last_error().
+ *  - Tile size is fixed at 16x16 (rasterizer/gsplat/config.h:1-2; it leaks into the callers,
+ *    model.cpp:144, simple_trainer.cpp:91).  tiles_x = ceil(W/16), tiles_y = ceil(H/16).
+ *  - Quaternions are stored (w,x,y,z) (helpers.cuh:145-153); viewmat/projmat are row-major 4x4.
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_TILE 16
+#define GSB_ERR_INVALID_ARG (-1)
+#define GSB_ERR_WORKSPACE (-2)
+#define GSB_ERR_UNSUPPORTED (-3)
+
+typedef void *gsb_stream_t; /* cudaStream_t */
+
+/* ABI version (major*100 + minor) and last error text for the calling thread. */
+int gsb_version(void);
+const char *gsb_last_error(void);
+
+/* ---- Spherical harmonics ---------------------------------------------------------------------
+ * gsb_sh_forward  replaces compute_sh_forward_tensor  (bindings.h:26-32, bindings.cu:68-92,
+ *                 kernel sh.cuh:218-238).   viewdirs [n,3], coeffs [n,K,3] with
+ *                 K = (degree+1)^2, degree in 0..4; colors [n,3].  viewdirs are normalised inside
+ *                 (sh.cuh:67-72).  degrees_to_use <= degree.
+ * gsb_sh_backward replaces compute_sh_backward_tensor (bindings.h:34-40, bindings.cu:94-124,
+ *                 kernel sh.cuh:240-260).   v_coeffs [n,K,3] is fully written (bases above
+ *                 degrees_to_use get 0, as the reference's torch::zeros).  No gradient w.r.t.
+ *                 viewdirs (spherical_harmonics.cpp:57-61). */
+int gsb_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *coeffs,
+                   float *colors, gsb_stream_t stream);
+int gsb_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *v_colors,
+                    float *v_coeffs, gsb_stream_t stream);
+
+/* ---- Projection ------------------------------------------------------------------------------
+ * gsb_project_forward replaces project_gaussians_forward_tensor (bindings.h:42-65,
+ *   bindings.cu:133-207, kernel forward.cu:19-103).  Outputs cov3d [n,6], xys [n,2], depths [n]
+ *   (view-space z), radii [n] i32 (0 == culled), conics [n,3], num_tiles_hit [n] i32; all fully
+ *   written (culled Gaussians get zeros, like the reference's torch::zeros).
+ * gsb_project_backward replaces project_gaussians_backward_tensor (bindings.h:67-92,
+ *   bindings.cu:209-277, kernel backward.cu:357-421).  v_depth may be NULL (== zeros).  cov3d is
+ *   accepted for signature parity and may be NULL (recomputed in registers).  Writes v_mean3d [n,3],
+ *   v_scale [n,3], v_quat [n,4] (zeros where radii <= 0).  Computes the exact VJP of the forward
+ *   map (see DESIGN.md "gradient conventions"). */
+int gsb_project_forward(int n, const float *means3d, const float *scales, float glob_scale,
+                        const float *quats, const float *viewmat, const float *projmat, float fx, float fy,
+                        float cx, float cy, int img_h, int img_w, int tiles_x, int tiles_y,
+                        float clip_thresh, float *cov3d, float *xys, float *depths, int32_t *radii,
+                        float *conics, int32_t *num_tiles_hit, gsb_stream_t stream);
+int gsb_project_backward(int n, const float *means3d, const float *scales, float glob_scale,
+                         const float *quats, const float *viewmat, const float *projmat, float fx, float fy,
+                         float cx, float cy, int img_h, int img_w, const float *cov3d,
+                         const int32_t *radii, const float *conics, const float *v_xy,
+                         const float *v_depth, const float *v_conic, float *v_mean3d, float *v_scale,
+                         float *v_quat, gsb_stream_t stream);
+
+/* ---- Tile binning ----------------------------------------------------------------------------
+ * gsb_cumsum_tiles_hit replaces torch::cumsum(numTilesHit, 0, kInt32) (rasterize_gaussians.cpp:62).
+ *   Inclusive scan; the caller reads M = cum_tiles_hit[n-1] back (rasterize_gaussians.cpp:63).
+ *   If total_out != NULL the total is also written there (device or mapped-pinned int32).
+ * gsb_map_gaussian_to_intersects replaces map_gaussian_to_intersects_tensor (bindings.h:95-103,
+ *   bindings.cu:279-318, kernel forward.cu:107-143): isect_ids [m] i64 = (tile_id << 32) | depth bits,
+ *   gaussian_ids [m] i32.
+ * gsb_sort_intersects replaces torch::sort(isectIds) (rasterize_gaussians.cpp:25-29): STABLE
+ *   ascending sort; writes sorted keys and the permutation (int32 instead of torch's int64).
+ *   Only bits [0, 32 + ceil(log2(num_tiles))) of the keys are examined.
+ * gsb_gather_bin_edges replaces torch::gather(gaussianIds, 0, sortedIndices)
+ *   (rasterize_gaussians.cpp:32) + get_tile_bin_edges_tensor (bindings.h:105-108,
+ *   bindings.cu:320-336, kernel forward.cu:148-169).  tile_bins is [num_tiles,2] i32 (x = first,
+ *   y = last+1; empty tiles (0,0)), fully written. */
+size_t gsb_cumsum_workspace_bytes(int n);
+int gsb_cumsum_tiles_hit(int n, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit, void *workspace,
+                         size_t workspace_bytes, int32_t *total_out, gsb_stream_t stream);
+int gsb_map_gaussian_to_intersects(int n, int m, const float *xys, const float *depths,
+                                   const int32_t *radii, const int32_t *cum_tiles_hit, int tiles_x,
+                                   int tiles_y, int64_t *isect_ids, int32_t *gaussian_ids,
+                                   gsb_stream_t stream);
+size_t gsb_sort_workspace_bytes(int m);
+int gsb_sort_intersects(int m, int num_tiles, const int64_t *isect_ids, int64_t *isect_ids_sorted,
+                        int32_t *sorted_index, void *workspace, size_t workspace_bytes,
+                        gsb_stream_t stream);
+int gsb_gather_bin_edges(int m, int num_tiles, const int64_t *isect_ids_sorted,
+                         const int32_t *sorted_index, const int32_t *gaussian_ids,
+                         int32_t *gaussian_ids_sorted, int32_t *tile_bins, gsb_stream_t stream);
+
+/* ---- Rasterization ---------------------------------------------------------------------------
+ * gsb_rasterize_forward replaces rasterize_forward_tensor (bindings.h:110-125, bindings.cu:338-410,
+ *   kernel forward.cu:256-378).  Inputs as the reference (gaussian_ids_sorted [m], tile_bins
+ *   [tiles,2], xys [n,2], conics [n,3], colors [n,3], opacities [n], background [3] on device) plus
+ *   sorted_index [m] (the permutation from gsb_sort_intersects: sorted position -> unsorted
+ *   intersection slot).  `records` is a caller-provided buffer of gsb_raster_records_bytes(m): the
+ *   call packs the depth-sorted per-intersection stream (48 B/intersection) that the blend kernel
+ *   pulls with TMA bulk copies; keep it for the backward pass.  Outputs out_img [H,W,3],
+ *   final_Ts [H,W], final_idx [H,W] i32, fully written.
+ * gsb_rasterize_backward replaces rasterize_backward_tensor (bindings.h:174-189,
+ *   bindings.cu:569-632, kernel backward.cu:161-355).  Consumes `records` from the forward call,
+ *   cum_tiles_hit [n] (gsb_cumsum_tiles_hit) and a scratch buffer grad_rows of
+ *   gsb_raster_grad_rows_bytes(m).  v_output [H,W,3]; v_output_alpha [H,W] may be NULL (== zeros,
+ *   rasterize_gaussians.cpp:108).  Writes v_xy [n,2], v_conic [n,3], v_colors [n,3], v_opacity [n]
+ *   completely (no atomics, bit-reproducible run to run). */
+size_t gsb_raster_records_bytes(int m);
+size_t gsb_raster_grad_rows_bytes(int m);
+int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tiles_y, int m,
+                          const int32_t *gaussian_ids_sorted, const int32_t *sorted_index,
+                          const int32_t *tile_bins, const float *xys, const float *conics,
+                          const float *colors, const float *opacities, const float *background,
+                          void *records, float *out_img, float *final_Ts, int32_t *final_idx,
+                          gsb_stream_t stream);
+int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
+                           const int32_t *tile_bins, const void *records,
+                           const int32_t *cum_tiles_hit, const float *background,
+                           const float *final_Ts, const int32_t *final_idx, const float *v_output,
+                           const float *v_output_alpha, void *grad_rows, float *v_xy, float *v_conic,
+                           float *v_colors, float *v_opacity, gsb_stream_t stream);
+
+/* ---- Streaming helpers around the path (SURVEY.md 8f "next" rows) ------------------------------
+ * gsb_mse_loss_grad: loss = mean((img-target)^2) accumulated into *loss_out (device float, caller
+ *   zeroes it) and v_img = 2 (img-target) * inv_count, one pass (simple_trainer.cpp:199-201:
+ *   torch::nn::MSELoss + autograd).  n = number of floats, inv_count = 1/n.
+ * gsb_adam_step: fused Adam over a flat fp32 buffer, semantics of torch::optim::Adam without weight
+ *   decay / amsgrad (simple_trainer.cpp:146,202; model.cpp:236-243): bias_correction{1,2} = 1 - beta^t. */
+int gsb_mse_loss_grad(long long n, const float *img, const float *target, float *v_img, float *loss_out,
+                      float inv_count, gsb_stream_t stream);
+int gsb_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr,
+                  float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
+                  gsb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */

@@ -1,0 +1,109 @@
+// fused.cu -- small streaming kernels around the hot path ("next" rows of SURVEY.md section 8f):
+//   gsb_mse_loss_grad : loss = mean((img - target)^2) and v_img = 2 (img - target) / count in one pass
+//                       (simple_trainer.cpp:199-201 does this with torch::nn::MSELoss + autograd)
+//   gsb_adam_step     : one fused Adam update over a flat parameter buffer
+//                       (simple_trainer.cpp:146,202 torch::optim::Adam; model.cpp:236-243 runs six of them)
+// Both are HBM-bound elementwise passes: 128-bit accesses, grid = multiple of the SM count.
+#include "gsb_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+mse_loss_grad_kernel(long long n4, long long n, const float *__restrict__ img,
+                     const float *__restrict__ target, float *__restrict__ v_img,
+                     float *__restrict__ loss_out, float inv_count) {
+    float acc = 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 a = reinterpret_cast<const float4 *>(img)[i];
+        const float4 b = reinterpret_cast<const float4 *>(target)[i];
+        const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        acc += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+        const float s = 2.f * inv_count;
+        reinterpret_cast<float4 *>(v_img)[i] = make_float4(s * d.x, s * d.y, s * d.z, s * d.w);
+    }
+    // tail (n not a multiple of 4)
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float d = img[i] - target[i];
+        acc += d * d;
+        v_img[i] = 2.f * inv_count * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float v = sm[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(loss_out, v * inv_count);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(long long n4, long long n, float *__restrict__ p, const float *__restrict__ g,
+            float *__restrict__ m, float *__restrict__ v, float lr, float b1, float b2, float eps,
+            float inv_bc1, float inv_sqrt_bc2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto upd = [&](float &pp, float gg, float &mm, float &vv) {
+        mm = b1 * mm + (1.f - b1) * gg;
+        vv = b2 * vv + (1.f - b2) * gg * gg;
+        // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+        pp -= lr * inv_bc1 * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+    };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 P = reinterpret_cast<float4 *>(p)[i];
+        const float4 G = ldg_stream4(reinterpret_cast<const float4 *>(g) + i);
+        float4 M = reinterpret_cast<float4 *>(m)[i];
+        float4 V = reinterpret_cast<float4 *>(v)[i];
+        upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+        reinterpret_cast<float4 *>(p)[i] = P;
+        reinterpret_cast<float4 *>(m)[i] = M;
+        reinterpret_cast<float4 *>(v)[i] = V;
+    }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        upd(p[i], g[i], m[i], v[i]);
+}
+
+int sm_count() {
+    static thread_local int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+}  // namespace
+
+// loss_out (device float) is accumulated into: the caller zeroes it (or passes a zeroed slot).
+extern "C" int gsb_mse_loss_grad(long long n, const float *img, const float *target, float *v_img,
+                                 float *loss_out, float inv_count, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(img && target && v_img && loss_out);
+    const bool vec = (((uintptr_t)img | (uintptr_t)target | (uintptr_t)v_img) % 16) == 0;
+    const long long n4 = vec ? n / 4 : 0;
+    mse_loss_grad_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(n4, n, img, target, v_img, loss_out,
+                                                                        inv_count);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gsb_adam_step(long long n, float *param, const float *grad, float *exp_avg,
+                             float *exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                             float bias_correction1, float bias_correction2, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && bias_correction1 > 0.f && bias_correction2 > 0.f);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(param && grad && exp_avg && exp_avg_sq);
+    const bool vec = (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) == 0;
+    const long long n4 = vec ? n / 4 : 0;
+    adam_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(n4, n, param, grad, exp_avg, exp_avg_sq, lr, beta1,
+                                                               beta2, eps, 1.f / bias_correction1,
+                                                               1.f / sqrtf(bias_correction2));
+    GSB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,210 @@
+// sh.cu -- spherical-harmonics colour evaluation, forward + VJP (S1/S2 of SURVEY.md section 8a).
+//
+// Replaces compute_sh_forward_kernel / compute_sh_backward_kernel (reference
+// rasterizer/gsplat/sh.cuh:218-260, math :52-216).  Pure streaming work: 12+12K+12 bytes per
+// Gaussian each way (K = number of SH bases), HBM-bound.  The reference reads the [N,K,3] AoS
+// coefficient block with one thread per Gaussian (192-B stride between lanes at K=16).  Here a CTA
+// moves its 128 Gaussians' coefficients as one contiguous span with 128-bit streaming accesses
+// (fully coalesced, L1 bypassed) through a padded shared-memory transpose; rows are padded to
+// 4*odd floats so the per-thread 128-bit row reads are bank-conflict free.
+#include "gsb_common.cuh"
+
+namespace {
+
+constexpr int SH_THREADS = 128;
+
+__host__ __device__ constexpr int sh_row_stride(int K) {
+    int q = (3 * K + 3) / 4;
+    return 4 * ((q & 1) ? q : q + 1);
+}
+
+// SH constants, sh.cuh:12-37
+__device__ __forceinline__ void sh_basis(int nb, float vx, float vy, float vz, float *Y) {
+    Y[0] = 0.28209479177387814f;
+    if (nb <= 1) return;
+    // sh.cuh:67-72 normalises the direction inside the kernel
+    float norm = sqrtf(vx * vx + vy * vy + vz * vz);
+    float x = vx / norm, y = vy / norm, z = vz / norm;
+    float xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+    Y[1] = -0.4886025119029199f * y;
+    Y[2] = 0.4886025119029199f * z;
+    Y[3] = -0.4886025119029199f * x;
+    if (nb <= 4) return;
+    Y[4] = 1.0925484305920792f * xy;
+    Y[5] = -1.0925484305920792f * yz;
+    Y[6] = 0.31539156525252005f * (2.f * zz - xx - yy);
+    Y[7] = -1.0925484305920792f * xz;
+    Y[8] = 0.5462742152960396f * (xx - yy);
+    if (nb <= 9) return;
+    Y[9] = -0.5900435899266435f * y * (3.f * xx - yy);
+    Y[10] = 2.890611442640554f * xy * z;
+    Y[11] = -0.4570457994644658f * y * (4.f * zz - xx - yy);
+    Y[12] = 0.3731763325901154f * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    Y[13] = -0.4570457994644658f * x * (4.f * zz - xx - yy);
+    Y[14] = 1.445305721320277f * z * (xx - yy);
+    Y[15] = -0.5900435899266435f * x * (xx - 3.f * yy);
+    if (nb <= 16) return;
+    Y[16] = 2.5033429417967046f * xy * (xx - yy);
+    Y[17] = -1.7701307697799304f * yz * (3.f * xx - yy);
+    Y[18] = 0.9461746957575601f * xy * (7.f * zz - 1.f);
+    Y[19] = -0.6690465435572892f * yz * (7.f * zz - 3.f);
+    Y[20] = 0.10578554691520431f * (zz * (35.f * zz - 30.f) + 3.f);
+    Y[21] = -0.6690465435572892f * xz * (7.f * zz - 3.f);
+    Y[22] = 0.47308734787878004f * (xx - yy) * (7.f * zz - 1.f);
+    Y[23] = -1.7701307697799304f * xz * (xx - 3.f * yy);
+    Y[24] = 0.6258357354491761f * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
+}
+
+__device__ __forceinline__ int nb_of(int degrees_to_use) {
+    return (degrees_to_use + 1) * (degrees_to_use + 1);
+}
+
+template <int K>
+__global__ void __launch_bounds__(SH_THREADS)
+sh_forward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
+                  const float *__restrict__ coeffs, float *__restrict__ colors, int vec_ok) {
+    constexpr int C = 3 * K;
+    constexpr int S = sh_row_stride(K);
+    __shared__ __align__(16) float tile[SH_THREADS * S];
+    const int g0 = blockIdx.x * SH_THREADS;
+    const int ng = min(SH_THREADS, n - g0);
+    const int nb = min(nb_of(degrees_to_use), K);
+    const float *src = coeffs + (size_t)g0 * C;
+    const int total = ng * C;
+    // ---- coalesced span load -> padded rows ----
+    if (vec_ok && (C % 4 == 0)) {
+        const float4 *src4 = reinterpret_cast<const float4 *>(src);
+        for (int f = threadIdx.x; f < total / 4; f += SH_THREADS) {
+            float4 v = ldg_stream4(src4 + f);
+            int e = 4 * f, g = e / C, j = e - g * C;
+            *reinterpret_cast<float4 *>(&tile[g * S + j]) = v;
+        }
+    } else {
+        for (int e = threadIdx.x; e < total; e += SH_THREADS) {
+            int g = e / C, j = e - g * C;
+            tile[g * S + j] = __ldg(src + e);
+        }
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= ng) return;
+    const int g = g0 + t;
+    float Y[K];
+    sh_basis(nb, viewdirs[3 * g], viewdirs[3 * g + 1], viewdirs[3 * g + 2], Y);
+    float row[S];
+#pragma unroll
+    for (int j = 0; j < S; j += 4) {
+        float4 v = *reinterpret_cast<const float4 *>(&tile[t * S + j]);
+        row[j] = v.x; row[j + 1] = v.y; row[j + 2] = v.z; row[j + 3] = v.w;
+    }
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+        if (b < nb) {
+            c0 += Y[b] * row[3 * b];
+            c1 += Y[b] * row[3 * b + 1];
+            c2 += Y[b] * row[3 * b + 2];
+        }
+    }
+    colors[3 * g] = c0;
+    colors[3 * g + 1] = c1;
+    colors[3 * g + 2] = c2;
+}
+
+template <int K>
+__global__ void __launch_bounds__(SH_THREADS)
+sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
+                   const float *__restrict__ v_colors, float *__restrict__ v_coeffs, int vec_ok) {
+    constexpr int C = 3 * K;
+    constexpr int S = sh_row_stride(K);
+    __shared__ __align__(16) float tile[SH_THREADS * S];
+    const int g0 = blockIdx.x * SH_THREADS;
+    const int ng = min(SH_THREADS, n - g0);
+    const int nb = min(nb_of(degrees_to_use), K);
+    const int t = threadIdx.x;
+    if (t < ng) {
+        const int g = g0 + t;
+        float Y[K];
+        sh_basis(nb, viewdirs[3 * g], viewdirs[3 * g + 1], viewdirs[3 * g + 2], Y);
+        const float v0 = v_colors[3 * g], v1 = v_colors[3 * g + 1], v2 = v_colors[3 * g + 2];
+        float row[S];
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            float yb = (b < nb) ? Y[b] : 0.f;  // bases above degrees_to_use stay 0 (bindings.cu:110)
+            row[3 * b] = yb * v0;
+            row[3 * b + 1] = yb * v1;
+            row[3 * b + 2] = yb * v2;
+        }
+#pragma unroll
+        for (int j = C; j < S; ++j) row[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < S; j += 4)
+            *reinterpret_cast<float4 *>(&tile[t * S + j]) = make_float4(row[j], row[j + 1], row[j + 2], row[j + 3]);
+    }
+    __syncthreads();
+    float *dst = v_coeffs + (size_t)g0 * C;
+    const int total = ng * C;
+    if (vec_ok && (C % 4 == 0)) {
+        float4 *dst4 = reinterpret_cast<float4 *>(dst);
+        for (int f = threadIdx.x; f < total / 4; f += SH_THREADS) {
+            int e = 4 * f, g = e / C, j = e - g * C;
+            stg_stream4(dst4 + f, *reinterpret_cast<const float4 *>(&tile[g * S + j]));
+        }
+    } else {
+        for (int e = threadIdx.x; e < total; e += SH_THREADS) {
+            int g = e / C, j = e - g * C;
+            dst[e] = tile[g * S + j];
+        }
+    }
+}
+
+int bases_of_degree(int degree) {
+    switch (degree) {
+        case 0: return 1;
+        case 1: return 4;
+        case 2: return 9;
+        case 3: return 16;
+        case 4: return 25;
+        default: return -1;
+    }
+}
+
+}  // namespace
+
+extern "C" int gsb_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs,
+                              const float *coeffs, float *colors, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(viewdirs && coeffs && colors);
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = gsb_div_up(n, SH_THREADS);
+    int vec_ok = ((uintptr_t)coeffs % 16) == 0;
+    switch (degree) {
+        case 0: sh_forward_kernel<1><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
+        case 1: sh_forward_kernel<4><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
+        case 2: sh_forward_kernel<9><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
+        case 3: sh_forward_kernel<16><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
+        default: sh_forward_kernel<25><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
+    }
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gsb_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs,
+                               const float *v_colors, float *v_coeffs, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(viewdirs && v_colors && v_coeffs);
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = gsb_div_up(n, SH_THREADS);
+    int vec_ok = ((uintptr_t)v_coeffs % 16) == 0;
+    switch (degree) {
+        case 0: sh_backward_kernel<1><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
+        case 1: sh_backward_kernel<4><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
+        case 2: sh_backward_kernel<9><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
+        case 3: sh_backward_kernel<16><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
+        default: sh_backward_kernel<25><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
+    }
+    GSB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,291 @@
+"""Python mirror of the reference's autograd operator layer, on top of the C ABI.
+
+Same class names, argument order/meaning and error behaviour as the reference's libtorch operators
+(/root/reference):
+  ProjectGaussians     project_gaussians.hpp:12-30,  project_gaussians.cpp:5-90
+  RasterizeGaussians   rasterize_gaussians.hpp:22-37, rasterize_gaussians.cpp:39-140
+  binAndSortGaussians  rasterize_gaussians.hpp:11-19, rasterize_gaussians.cpp:6-37
+  SphericalHarmonics   spherical_harmonics.hpp:15-23, spherical_harmonics.cpp:32-63
+The C++/libtorch version of this layer (the actual drop-in for model.cpp / simple_trainer.cpp) is in
+opensplat_b200/csrc/ops; this module is what the parity tests and bench.py drive.
+
+All compute happens in libgsplat_b200.so (hand-written sm_100a CUDA); torch supplies memory, streams
+and the autograd graph.  CPU tensors are rejected -- there is no fallback path.
+"""
+import torch
+
+from . import capi
+
+BLOCK_X = 16  # rasterizer/gsplat/config.h:1-2
+BLOCK_Y = 16
+
+
+def tile_bounds(width, height):
+    """TileBounds as the callers compute it (model.cpp:144, simple_trainer.cpp:91)."""
+    return ((width + BLOCK_X - 1) // BLOCK_X, (height + BLOCK_Y - 1) // BLOCK_Y, 1)
+
+
+def deg_from_sh(num_bases):  # spherical_harmonics.cpp:3-16
+    return {1: 0, 4: 1, 9: 2, 16: 3}.get(int(num_bases), 4)
+
+
+def num_sh_bases(degree):  # sh.cuh:40-50
+    return {0: 1, 1: 4, 2: 9, 3: 16}.get(int(degree), 25)
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+class _Workspace:
+    """Grow-only device scratch buffers keyed by (device, tag): avoids a cudaMalloc per call
+    (the reference pays ~20 torch::zeros allocations per iteration)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, device, tag, nbytes):
+        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        b = self.bufs.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+            self.bufs[key] = b
+        return b
+
+
+_ws = _Workspace()
+
+
+# ------------------------------------------------------------------------------------------------
+# functional layer (one call per C-ABI entry point; mirrors bindings.h `*_tensor` functions)
+# ------------------------------------------------------------------------------------------------
+def compute_sh_forward(degree, degrees_to_use, viewdirs, coeffs):
+    n = coeffs.shape[0]
+    nb = num_sh_bases(degree)
+    if coeffs.dim() != 3 or coeffs.shape[1] != nb or coeffs.shape[2] != 3:
+        raise ValueError("coeffs must have dimensions (N, D, 3)")  # bindings.cu:76-79
+    viewdirs, coeffs = capi.f32(viewdirs), capi.f32(coeffs)
+    colors = _empty((n, 3), torch.float32, coeffs)
+    capi.check(capi.lib().gsb_sh_forward(n, degree, degrees_to_use, capi.ptr(viewdirs), capi.ptr(coeffs),
+                                         capi.ptr(colors), capi.stream()))
+    return colors
+
+
+def compute_sh_backward(degree, degrees_to_use, viewdirs, v_colors):
+    n = v_colors.shape[0]
+    if viewdirs.dim() != 2 or viewdirs.shape[0] != n or viewdirs.shape[1] != 3:
+        raise ValueError("viewdirs must have dimensions (N, 3)")  # bindings.cu:101-104
+    if v_colors.dim() != 2 or v_colors.shape[1] != 3:
+        raise ValueError("v_colors must have dimensions (N, 3)")
+    viewdirs, v_colors = capi.f32(viewdirs), capi.f32(v_colors)
+    v_coeffs = _empty((n, num_sh_bases(degree), 3), torch.float32, v_colors)
+    capi.check(capi.lib().gsb_sh_backward(n, degree, degrees_to_use, capi.ptr(viewdirs), capi.ptr(v_colors),
+                                          capi.ptr(v_coeffs), capi.stream()))
+    return v_coeffs
+
+
+def project_gaussians_forward(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy,
+                              img_height, img_width, tile_bounds_, clip_thresh=0.01):
+    n = means3d.shape[0]
+    means3d, scales, quats = capi.f32(means3d), capi.f32(scales), capi.f32(quats)
+    viewmat, projmat = capi.f32(viewmat), capi.f32(projmat)
+    cov3d = _empty((n, 6), torch.float32, means3d)
+    xys = _empty((n, 2), torch.float32, means3d)
+    depths = _empty((n,), torch.float32, means3d)
+    radii = _empty((n,), torch.int32, means3d)
+    conics = _empty((n, 3), torch.float32, means3d)
+    nth = _empty((n,), torch.int32, means3d)
+    capi.check(capi.lib().gsb_project_forward(
+        n, capi.ptr(means3d), capi.ptr(scales), glob_scale, capi.ptr(quats), capi.ptr(viewmat),
+        capi.ptr(projmat), fx, fy, cx, cy, img_height, img_width, tile_bounds_[0], tile_bounds_[1],
+        clip_thresh, capi.ptr(cov3d), capi.ptr(xys), capi.ptr(depths), capi.ptr(radii), capi.ptr(conics),
+        capi.ptr(nth), capi.stream()))
+    return cov3d, xys, depths, radii, conics, nth
+
+
+def project_gaussians_backward(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy,
+                               img_height, img_width, cov3d, radii, conics, v_xy, v_depth, v_conic):
+    n = means3d.shape[0]
+    means3d, scales, quats = capi.f32(means3d), capi.f32(scales), capi.f32(quats)
+    viewmat, projmat = capi.f32(viewmat), capi.f32(projmat)
+    v_xy, v_conic = capi.f32(v_xy), capi.f32(v_conic)
+    v_depth = capi.f32(v_depth) if v_depth is not None else None
+    v_mean = _empty((n, 3), torch.float32, means3d)
+    v_scale = _empty((n, 3), torch.float32, means3d)
+    v_quat = _empty((n, 4), torch.float32, means3d)
+    capi.check(capi.lib().gsb_project_backward(
+        n, capi.ptr(means3d), capi.ptr(scales), glob_scale, capi.ptr(quats), capi.ptr(viewmat),
+        capi.ptr(projmat), fx, fy, cx, cy, img_height, img_width, None, capi.ptr(radii.contiguous()),
+        capi.ptr(capi.f32(conics)), capi.ptr(v_xy), capi.ptr(v_depth), capi.ptr(v_conic), capi.ptr(v_mean),
+        capi.ptr(v_scale), capi.ptr(v_quat), capi.stream()))
+    return v_mean, v_scale, v_quat
+
+
+def cumsum_tiles_hit(num_tiles_hit):
+    """torch::cumsum(numTilesHit, 0, kInt32) (rasterize_gaussians.cpp:62)."""
+    n = num_tiles_hit.shape[0]
+    num_tiles_hit = num_tiles_hit.contiguous()
+    cum = _empty((n,), torch.int32, num_tiles_hit)
+    L = capi.lib()
+    wsb = L.gsb_cumsum_workspace_bytes(n)
+    ws = _ws.get(num_tiles_hit.device, "cumsum", wsb)
+    capi.check(L.gsb_cumsum_tiles_hit(n, capi.ptr(num_tiles_hit), capi.ptr(cum), capi.ptr(ws), ws.numel(),
+                                      None, capi.stream()))
+    return cum
+
+
+def map_gaussian_to_intersects(num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds_):
+    isect = _empty((num_intersects,), torch.int64, xys)
+    gids = _empty((num_intersects,), torch.int32, xys)
+    capi.check(capi.lib().gsb_map_gaussian_to_intersects(
+        num_points, num_intersects, capi.ptr(capi.f32(xys)), capi.ptr(capi.f32(depths)),
+        capi.ptr(radii.contiguous()), capi.ptr(cum_tiles_hit.contiguous()), tile_bounds_[0], tile_bounds_[1],
+        capi.ptr(isect), capi.ptr(gids), capi.stream()))
+    return isect, gids
+
+
+def sort_intersects(isect_ids, num_tiles):
+    """torch::sort(isectIds) (rasterize_gaussians.cpp:25-29): returns (sorted keys, int32 permutation)."""
+    m = isect_ids.shape[0]
+    ks = torch.empty_like(isect_ids)
+    idx = _empty((m,), torch.int32, isect_ids)
+    L = capi.lib()
+    wsb = L.gsb_sort_workspace_bytes(m)
+    ws = _ws.get(isect_ids.device, "sort", wsb + 256)
+    off = (-ws.data_ptr()) % 256
+    capi.check(L.gsb_sort_intersects(m, num_tiles, capi.ptr(isect_ids.contiguous()), capi.ptr(ks), capi.ptr(idx),
+                                     ws.data_ptr() + off, ws.numel() - off, capi.stream()))
+    return ks, idx
+
+
+def gather_bin_edges(isect_ids_sorted, sorted_index, gaussian_ids, num_tiles):
+    m = isect_ids_sorted.shape[0]
+    gs = _empty((m,), torch.int32, isect_ids_sorted)
+    bins = _empty((num_tiles, 2), torch.int32, isect_ids_sorted)
+    capi.check(capi.lib().gsb_gather_bin_edges(m, num_tiles, capi.ptr(isect_ids_sorted), capi.ptr(sorted_index),
+                                               capi.ptr(gaussian_ids), capi.ptr(gs), capi.ptr(bins),
+                                               capi.stream()))
+    return gs, bins
+
+
+def binAndSortGaussians(numPoints, numIntersects, xys, depths, radii, cumTilesHit, tileBounds,
+                        return_index=False):
+    """rasterize_gaussians.cpp:6-37 -> (isectIds, gaussianIds, isectIdsSorted, gaussianIdsSorted, tileBins)."""
+    isect, gids = map_gaussian_to_intersects(numPoints, numIntersects, xys, depths, radii, cumTilesHit,
+                                             tileBounds)
+    num_tiles = tileBounds[0] * tileBounds[1]
+    ks, idx = sort_intersects(isect, num_tiles)
+    gs, bins = gather_bin_edges(ks, idx, gids, num_tiles)
+    if return_index:
+        return isect, gids, ks, gs, bins, idx
+    return isect, gids, ks, gs, bins
+
+
+def rasterize_forward(tile_bounds_, img_size, gaussian_ids_sorted, sorted_index, tile_bins, xys, conics,
+                      colors, opacities, background):
+    W, H = img_size[0], img_size[1]
+    m = gaussian_ids_sorted.shape[0]
+    L = capi.lib()
+    records = torch.empty(L.gsb_raster_records_bytes(m), dtype=torch.uint8, device=xys.device)
+    out = _empty((H, W, 3), torch.float32, xys)
+    fT = _empty((H, W), torch.float32, xys)
+    fI = _empty((H, W), torch.int32, xys)
+    if colors.shape[-1] != 3:
+        raise ValueError("only 3-channel colors are supported")  # the N-D path is dead code in OpenSplat
+    capi.check(L.gsb_rasterize_forward(
+        H, W, tile_bounds_[0], tile_bounds_[1], m, capi.ptr(gaussian_ids_sorted), capi.ptr(sorted_index),
+        capi.ptr(tile_bins), capi.ptr(capi.f32(xys)), capi.ptr(capi.f32(conics)), capi.ptr(capi.f32(colors)),
+        capi.ptr(capi.f32(opacities)), capi.ptr(capi.f32(background)), capi.ptr(records), capi.ptr(out),
+        capi.ptr(fT), capi.ptr(fI), capi.stream()))
+    return out, fT, fI, records
+
+
+def rasterize_backward(img_height, img_width, n, m, tile_bins, records, cum_tiles_hit, background, final_Ts,
+                       final_idx, v_output, v_output_alpha=None):
+    L = capi.lib()
+    tb = tile_bounds(img_width, img_height)
+    rows = _ws.get(final_Ts.device, "grad_rows", L.gsb_raster_grad_rows_bytes(m) + 16)
+    off = (-rows.data_ptr()) % 16
+    v_xy = _empty((n, 2), torch.float32, final_Ts)
+    v_conic = _empty((n, 3), torch.float32, final_Ts)
+    v_colors = _empty((n, 3), torch.float32, final_Ts)
+    v_opacity = _empty((n, 1), torch.float32, final_Ts)
+    v_output = capi.f32(v_output)
+    capi.check(L.gsb_rasterize_backward(
+        img_height, img_width, tb[0], tb[1], n, m, capi.ptr(tile_bins), capi.ptr(records),
+        capi.ptr(cum_tiles_hit), capi.ptr(capi.f32(background)), capi.ptr(final_Ts), capi.ptr(final_idx),
+        capi.ptr(v_output), capi.ptr(v_output_alpha) if v_output_alpha is not None else None,
+        rows.data_ptr() + off, capi.ptr(v_xy), capi.ptr(v_conic), capi.ptr(v_colors), capi.ptr(v_opacity),
+        capi.stream()))
+    return v_xy, v_conic, v_colors, v_opacity
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd operators (names and slots as the reference)
+# ------------------------------------------------------------------------------------------------
+class ProjectGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, scales, globScale, quats, viewMat, projMat, fx, fy, cx, cy, imgHeight, imgWidth,
+                tileBounds, clipThresh=0.01):
+        cov3d, xys, depths, radii, conics, nth = project_gaussians_forward(
+            means, scales, float(globScale), quats, viewMat, projMat, float(fx), float(fy), float(cx),
+            float(cy), int(imgHeight), int(imgWidth), tileBounds, float(clipThresh))
+        ctx.meta = (float(globScale), float(fx), float(fy), float(cx), float(cy), int(imgHeight), int(imgWidth))
+        ctx.save_for_backward(means, scales, quats, viewMat, projMat, cov3d, radii, conics)
+        ctx.mark_non_differentiable(radii, nth)
+        return xys, depths, radii, conics, nth, cov3d  # project_gaussians.cpp:44
+
+    @staticmethod
+    def backward(ctx, v_xys, v_depths, v_radii, v_conics, v_numTiles, v_cov3d):
+        means, scales, quats, viewMat, projMat, cov3d, radii, conics = ctx.saved_tensors
+        gs, fx, fy, cx, cy, H, W = ctx.meta
+        if v_xys is None:
+            v_xys = torch.zeros_like(means[:, :2])
+        if v_conics is None:
+            v_conics = torch.zeros_like(conics)
+        v_mean, v_scale, v_quat = project_gaussians_backward(
+            means, scales, gs, quats, viewMat, projMat, fx, fy, cx, cy, H, W, cov3d, radii, conics, v_xys,
+            v_depths, v_conics)
+        # 14 slots, grads only for means(0), scales(1), quats(3)  (project_gaussians.cpp:75-89)
+        return (v_mean, v_scale, None, v_quat) + (None,) * 10
+
+
+class RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, numTilesHit, colors, opacity, imgHeight, imgWidth, background):
+        numPoints = xys.shape[0]
+        tb = tile_bounds(imgWidth, imgHeight)
+        cum = cumsum_tiles_hit(numTilesHit)
+        # the one device->host read-back of the path (rasterize_gaussians.cpp:63)
+        numIntersects = int(cum[-1].item()) if numPoints > 0 else 0
+        _, _, _, gs, bins, idx = binAndSortGaussians(numPoints, numIntersects, xys, depths, radii, cum, tb,
+                                                     return_index=True)
+        out, fT, fI, records = rasterize_forward(tb, (imgWidth, imgHeight, 1), gs, idx, bins, xys, conics,
+                                                 colors, opacity, background)
+        ctx.meta = (int(imgHeight), int(imgWidth), numPoints, numIntersects)
+        ctx.save_for_backward(bins, records, cum, background, fT, fI)
+        return out
+
+    @staticmethod
+    def backward(ctx, v_outImg):
+        H, W, n, m = ctx.meta
+        bins, records, cum, background, fT, fI = ctx.saved_tensors
+        v_xy, v_conic, v_colors, v_opacity = rasterize_backward(H, W, n, m, bins, records, cum, background, fT, fI,
+                                                                v_outImg.contiguous(), None)
+        # 10 slots; grads for xys(0), conics(3), colors(5), opacity(6) (rasterize_gaussians.cpp:129-139)
+        return v_xy, None, None, v_conic, None, v_colors, v_opacity, None, None, None
+
+
+class SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degreesToUse, viewDirs, coeffs):
+        degree = deg_from_sh(coeffs.shape[-2])
+        ctx.meta = (int(degreesToUse), degree)
+        ctx.save_for_backward(viewDirs)
+        return compute_sh_forward(degree, int(degreesToUse), viewDirs, coeffs)
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        degreesToUse, degree = ctx.meta
+        (viewDirs,) = ctx.saved_tensors
+        return None, None, compute_sh_backward(degree, degreesToUse, viewDirs, v_colors.contiguous())

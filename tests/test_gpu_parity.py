@@ -1,0 +1,400 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI (opensplat_b200.capi / ops), against
+  (a) oracle/gsplat_oracle.c on the same seeded inputs (stage by stage),
+  (b) the committed golden vectors produced by the reference itself (tests/golden).
+Integer artefacts (radii, num_tiles_hit, M, keys, permutation, tile bins) must be BIT-EXACT.
+Floating point tolerances are those of SURVEY.md 8c and are written next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from opensplat_b200 import ops
+from opensplat_b200.scene import make_scene
+from util import load_golden, rel_l2, image_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------- SH
+@pytest.mark.parametrize("name", ["sh_deg3", "sh_deg4"])
+def test_sh_vs_golden_and_oracle(name):
+    g = load_golden(name)
+    deg = int(g["degree"])
+    K = (deg + 1) ** 2
+    for d in range(deg + 1):
+        col = ops.compute_sh_forward(deg, d, cu(g["viewdirs"]), cu(g["coeffs"]))
+        assert np.abs(npy(col) - g[f"ref_colors_d{d}"]).max() <= 2e-5          # vs reference
+        assert np.abs(npy(col) - orc.sh_forward(d, g["viewdirs"], g["coeffs"])).max() <= 5e-6  # vs oracle
+        vc = ops.compute_sh_backward(deg, d, cu(g["viewdirs"]), cu(g["wgt"]))
+        assert np.abs(npy(vc) - g[f"ref_v_coeffs_d{d}"]).max() <= 2e-6
+        assert np.all(npy(vc)[:, (d + 1) ** 2:, :] == 0)
+
+
+@pytest.mark.parametrize("n,deg", [(1, 0), (127, 1), (129, 2), (1000, 3), (257, 4)])
+def test_sh_ragged_sizes(n, deg):
+    rng = np.random.default_rng(n)
+    K = (deg + 1) ** 2
+    vd = rng.standard_normal((n, 3)).astype(np.float32)
+    co = rng.standard_normal((n, K, 3)).astype(np.float32)
+    vcol = rng.standard_normal((n, 3)).astype(np.float32)
+    col = ops.compute_sh_forward(deg, deg, cu(vd), cu(co))
+    assert np.abs(npy(col) - orc.sh_forward(deg, vd, co)).max() <= 1e-5
+    vc = ops.compute_sh_backward(deg, deg, cu(vd), cu(vcol))
+    assert np.abs(npy(vc) - orc.sh_backward(deg, K, vd, vcol)).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------- projection + bins
+def _scene(n, W, H, scale, opacity=(0.05, 0.35), seed=0, **kw):
+    return make_scene(n, W, H, scale=scale, sh_degree=0, opacity=opacity, seed=seed, **kw)
+
+
+def _project_gpu(sc):
+    tb = ops.tile_bounds(sc["W"], sc["H"])
+    return ops.project_gaussians_forward(cu(sc["means"]), cu(sc["scales"]), 1.0, cu(sc["quats"]),
+                                         cu(sc["viewmat"]), cu(sc["projmat"]), sc["fx"], sc["fy"], sc["cx"],
+                                         sc["cy"], sc["H"], sc["W"], tb)
+
+
+def _project_orc(sc):
+    return orc.project_forward(sc["means"], sc["scales"], 1.0, sc["quats"], sc["viewmat"], sc["projmat"],
+                               sc["fx"], sc["fy"], sc["cx"], sc["cy"], sc["H"], sc["W"])
+
+
+@pytest.mark.parametrize("n,W,H,scale", [(5000, 256, 256, 0.3), (20000, 500, 300, 0.2), (3, 33, 17, 1.0)])
+def test_projection_forward_bit_exact(n, W, H, scale):
+    sc = _scene(n, W, H, scale, seed=n)
+    # push some Gaussians behind the near plane / off screen to exercise the culls
+    sc["means"][: n // 10, 2] = -9.0
+    sc["means"][n // 10: n // 5, 0] = 5.0
+    cov3d, xys, depths, radii, conics, nth = _project_gpu(sc)
+    o = _project_orc(sc)
+    assert np.array_equal(npy(radii), o["radii"])                 # bit-exact
+    assert np.array_equal(npy(nth), o["num_tiles_hit"])           # bit-exact
+    # the float chain is correctly-rounded op-for-op on both sides -> also bit-exact
+    assert np.array_equal(npy(xys), o["xys"])
+    assert np.array_equal(npy(depths), o["depths"])
+    assert np.array_equal(npy(conics), o["conics"])
+    assert np.array_equal(npy(cov3d), o["cov3d"])
+    assert (o["radii"] == 0).sum() >= n // 5
+
+
+@pytest.mark.parametrize("n,W,H,scale", [(4000, 256, 256, 0.3), (30000, 640, 360, 0.15), (50, 48, 40, 2.0)])
+def test_binning_bit_exact(n, W, H, scale):
+    sc = _scene(n, W, H, scale, seed=7 * n)
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    o = _project_orc(sc)
+    cum = ops.cumsum_tiles_hit(nth)
+    ocum, m = orc.cumsum(o["num_tiles_hit"])
+    assert np.array_equal(npy(cum), ocum) and int(cum[-1]) == m
+    tb = ops.tile_bounds(W, H)
+    isect, gids, ks, gs, bins, idx = ops.binAndSortGaussians(n, m, xys, depths, radii, cum, tb, return_index=True)
+    ob = orc.bin_and_sort(o["xys"], o["depths"], o["radii"], ocum, H, W)
+    assert np.array_equal(npy(isect), ob["isect_ids"])
+    assert np.array_equal(npy(gids), ob["gaussian_ids"])
+    assert np.array_equal(npy(ks), ob["isect_ids_sorted"])
+    assert np.array_equal(npy(idx), ob["sorted_index"])           # stable: ties keep ascending index
+    assert np.array_equal(npy(gs), ob["gaussian_ids_sorted"])
+    assert np.array_equal(npy(bins), ob["tile_bins"])
+
+
+def test_sort_stability_with_duplicate_keys():
+    # many identical (tile, depth) keys: the permutation must be the stable one
+    rng = np.random.default_rng(0)
+    m = 100_003
+    keys = (rng.integers(0, 37, m).astype(np.int64) << 32) | rng.integers(0, 5, m).astype(np.int64)
+    ks, idx = ops.sort_intersects(cu(keys), 37)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(npy(idx), order.astype(np.int32))
+    assert np.array_equal(npy(ks), keys[order])
+
+
+@pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 100_000, 1_000_003])
+def test_cumsum_sizes(n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 9, n).astype(np.int32)
+    cum = ops.cumsum_tiles_hit(cu(a))
+    assert np.array_equal(npy(cum), np.cumsum(a, dtype=np.int64).astype(np.int32))
+
+
+# ---------------------------------------------------------------------------------- rasterization
+def _raster_both(sc, colors, background, exp_mode=1):
+    n, W, H = sc["means"].shape[0], sc["W"], sc["H"]
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    cum = ops.cumsum_tiles_hit(nth)
+    m = int(cum[-1])
+    tb = ops.tile_bounds(W, H)
+    _, _, _, gs, bins, idx = ops.binAndSortGaussians(n, m, xys, depths, radii, cum, tb, return_index=True)
+    bg = cu(np.asarray(background, np.float32))
+    out, fT, fI, rec = ops.rasterize_forward(tb, (W, H, 1), gs, idx, bins, xys, conics, cu(colors),
+                                             cu(sc["opacities"]), bg)
+    o = orc.rasterize_forward(H, W, npy(gs), npy(bins), npy(xys), npy(conics), colors, sc["opacities"],
+                              background, exp_mode=exp_mode)
+    st = dict(n=n, m=m, tb=tb, gs=gs, bins=bins, idx=idx, xys=xys, conics=conics, cum=cum, bg=bg, rec=rec)
+    return (out, fT, fI), o, st
+
+
+@pytest.mark.parametrize("n,W,H,scale,opac,bg", [
+    (3000, 256, 256, 0.35, (0.05, 0.35), [0, 0, 0]),
+    (2000, 200, 120, 0.5, (0.3, 0.95), [0.6130, 0.0101, 0.3984]),   # ragged tiles + magenta background
+    (6000, 128, 128, 0.6, (0.7, 0.99), [1, 1, 1]),                  # saturating pixels: early termination
+])
+def test_rasterize_forward_backward_vs_oracle(n, W, H, scale, opac, bg):
+    sc = _scene(n, W, H, scale, opacity=opac, seed=n + W)
+    rng = np.random.default_rng(1)
+    colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    (out, fT, fI), o, st = _raster_both(sc, colors, bg)
+    # image: 1e-5 on all but isolated alpha-threshold flips (<= 1/255); kernel uses ex2.approx
+    ok, stats = image_close(npy(out), o["out_img"], tol=1e-5, frac=1e-3)
+    assert ok, stats
+    assert np.abs(npy(fT) - o["final_Ts"]).max() <= 4.5e-3
+    assert (npy(fI) != o["final_idx"]).mean() <= 1e-3            # identical except at threshold flips
+    if opac[0] >= 0.7:
+        assert (o["final_Ts"] < 1e-3).mean() > 0.2                 # the early-out path really ran
+    # backward on the oracle's own final_Ts/final_idx (identical inputs to both sides)
+    wgt = rng.uniform(-1, 1, (H, W, 3)).astype(np.float32)
+    fTo, fIo = cu(o["final_Ts"]), cu(o["final_idx"])
+    v = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["rec"], st["cum"], st["bg"], fTo, fIo, cu(wgt))
+    ob = orc.rasterize_backward(H, W, npy(st["gs"]), npy(st["bins"]), npy(st["xys"]), npy(st["conics"]), colors,
+                                sc["opacities"], bg, o["final_Ts"], o["final_idx"], wgt, exp_mode=1)
+    tol = 2e-4 if opac[1] < 0.9 else 2e-3   # fp32 re-association; 1/(1-alpha) amplifies when alpha -> 0.99
+    for a, b in zip(v, (ob["v_xy"], ob["v_conic"], ob["v_colors"], ob["v_opacity"])):
+        assert rel_l2(npy(a), b) <= tol
+    # deterministic: bit-identical on a second run (no atomics)
+    v2 = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["rec"], st["cum"], st["bg"], fTo, fIo, cu(wgt))
+    for a, b in zip(v, v2):
+        assert torch.equal(a, b)
+
+
+def test_rasterize_v_output_alpha_term():
+    n, W, H = 1500, 96, 96
+    sc = _scene(n, W, H, 0.5, seed=11)
+    rng = np.random.default_rng(2)
+    colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    (out, fT, fI), o, st = _raster_both(sc, colors, [0.2, 0.3, 0.4])
+    wgt = rng.uniform(-1, 1, (H, W, 3)).astype(np.float32)
+    wa = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+    v = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["rec"], st["cum"], st["bg"], cu(o["final_Ts"]),
+                               cu(o["final_idx"]), cu(wgt), cu(wa))
+    ob = orc.rasterize_backward(H, W, npy(st["gs"]), npy(st["bins"]), npy(st["xys"]), npy(st["conics"]), colors,
+                                sc["opacities"], [0.2, 0.3, 0.4], o["final_Ts"], o["final_idx"], wgt, wa, exp_mode=1)
+    for a, b in zip(v, (ob["v_xy"], ob["v_conic"], ob["v_colors"], ob["v_opacity"])):
+        assert rel_l2(npy(a), b) <= 2e-4
+
+
+def test_projection_backward_vs_oracle():
+    n, W, H = 5000, 256, 192
+    sc = _scene(n, W, H, 0.3, seed=5)
+    rng = np.random.default_rng(3)
+    sc["quats"] = (sc["quats"] * rng.uniform(0.5, 2, (n, 1))).astype(np.float32)  # raw quats (D11)
+    cov3d, xys, depths, radii, conics, nth = _project_gpu(sc)
+    v_xy = rng.standard_normal((n, 2)).astype(np.float32)
+    v_depth = rng.standard_normal((n,)).astype(np.float32)
+    v_conic = rng.standard_normal((n, 3)).astype(np.float32)
+    g = ops.project_gaussians_backward(cu(sc["means"]), cu(sc["scales"]), 1.0, cu(sc["quats"]), cu(sc["viewmat"]),
+                                       cu(sc["projmat"]), sc["fx"], sc["fy"], sc["cx"], sc["cy"], H, W, cov3d,
+                                       radii, conics, cu(v_xy), cu(v_depth), cu(v_conic))
+    o = orc.project_backward(sc["means"], sc["scales"], 1.0, sc["quats"], sc["viewmat"], sc["projmat"],
+                             sc["fx"], sc["fy"], sc["cx"], sc["cy"], H, W, npy(radii), npy(conics), v_xy, v_depth,
+                             v_conic)
+    # same formulas, both without FMA contraction: 1e-6 relative
+    assert rel_l2(npy(g[0]), o["v_mean3d"]) <= 1e-6
+    assert rel_l2(npy(g[1]), o["v_scale"]) <= 1e-6
+    assert rel_l2(npy(g[2]), o["v_quat"]) <= 1e-6
+
+
+def test_projection_backward_vs_torch_autograd_of_forward():
+    """fp32 torch restatement of OUR forward formula, differentiated by autograd (general P*V camera,
+    glob_scale != 1): checks the hand VJP is the exact gradient of the forward map."""
+    n, W, H = 2000, 320, 200
+    sc = _scene(n, W, H, 0.3, seed=9)
+    dev = DEV
+    means = cu(sc["means"]).double().requires_grad_()
+    scales = cu(sc["scales"]).double().requires_grad_()
+    quats = (cu(sc["quats"]) * 1.7).double().requires_grad_()
+    V = cu(sc["viewmat"]).double()
+    a = 0.3
+    V[:3, :3] = torch.tensor([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], device=dev)
+    fx, fy, cx, cy, gsc = sc["fx"] * 0.9, sc["fy"] * 1.1, W / 2 + 3.0, H / 2 - 2.0, 1.3
+    fovx, fovy = 2 * np.arctan(W / (2 * fx)), 2 * np.arctan(H / (2 * fy))
+    zn, zf = 0.001, 1000.0
+    t, r = zn * np.tan(0.5 * fovy), zn * np.tan(0.5 * fovx)
+    Pm = torch.tensor([[zn / r, 0, 0, 0], [0, zn / t, 0, 0], [0, 0, (zf + zn) / (zf - zn), -zf * zn / (zf - zn)],
+                       [0, 0, 1, 0]], device=dev, dtype=torch.float64)
+    P = Pm @ V
+
+    def fwd(means, scales, quats):
+        tview = means @ V[:3, :3].T + V[:3, 3]
+        qn = quats / quats.norm(dim=-1, keepdim=True)
+        w, x, y, z = qn.unbind(-1)
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                         2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                         2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+        M = R * (gsc * scales)[:, None, :]
+        cov3 = M @ M.transpose(1, 2)
+        tanx, tany = 0.5 * W / fx, 0.5 * H / fy
+        tz = tview[:, 2]
+        ttx = tz * torch.clamp(tview[:, 0] / tz, -1.3 * tanx, 1.3 * tanx)
+        tty = tz * torch.clamp(tview[:, 1] / tz, -1.3 * tany, 1.3 * tany)
+        rz = 1 / tz
+        zero = torch.zeros_like(rz)
+        J = torch.stack([fx * rz, zero, -fx * ttx * rz * rz, zero, fy * rz, -fy * tty * rz * rz], -1).reshape(-1, 2, 3)
+        T = J @ V[:3, :3]
+        cov2 = T @ cov3 @ T.transpose(1, 2)
+        cxx, cxy, cyy = cov2[:, 0, 0] + 0.3, cov2[:, 0, 1], cov2[:, 1, 1] + 0.3
+        det = cxx * cyy - cxy * cxy
+        conic = torch.stack([cyy / det, -cxy / det, cxx / det], -1)
+        hom = means @ P[:, :3].T + P[:, 3]
+        rw = 1 / (hom[:, 3] + 1e-6)
+        xy = torch.stack([0.5 * W * hom[:, 0] * rw + cx - 0.5, 0.5 * H * hom[:, 1] * rw + cy - 0.5], -1)
+        return xy, tz, conic
+
+    xy, tz, conic = fwd(means, scales, quats)
+    rng = np.random.default_rng(4)
+    v_xy, v_d, v_c = (cu(rng.standard_normal(s).astype(np.float32)) for s in [(n, 2), (n,), (n, 3)])
+    (xy * v_xy.double()).sum().add((tz * v_d.double()).sum()).add((conic * v_c.double()).sum()).backward()
+    tb = ops.tile_bounds(W, H)
+    f32 = lambda t: t.detach().float().contiguous()
+    cov3d, xys, depths, radii, conics, nth = ops.project_gaussians_forward(
+        f32(means), f32(scales), gsc, f32(quats), f32(V), f32(P), fx, fy, cx, cy, H, W, tb)
+    vis = npy(radii) > 0
+    assert vis.mean() > 0.5
+    assert np.abs(npy(xys)[vis] - npy(xy)[vis]).max() <= 2e-3 and rel_l2(npy(conics)[vis], npy(conic)[vis]) <= 1e-5
+    g = ops.project_gaussians_backward(f32(means), f32(scales), gsc, f32(quats), f32(V), f32(P), fx, fy, cx, cy, H,
+                                       W, cov3d, radii, conics, v_xy, v_d, v_c)
+    assert rel_l2(npy(g[0])[vis], npy(means.grad)[vis]) <= 2e-4
+    assert rel_l2(npy(g[1])[vis], npy(scales.grad)[vis]) <= 2e-4
+    assert rel_l2(npy(g[2])[vis], npy(quats.grad)[vis]) <= 2e-4
+    assert np.all(npy(g[0])[~vis] == 0) and np.all(npy(g[2])[~vis] == 0)
+
+
+# ------------------------------------------------------- operators end to end vs the reference itself
+@pytest.mark.parametrize("name,gtol,itol", [("chain_tight_100x72", 2e-3, 5e-5), ("chain_bg_quat_128x96", 2e-3, 5e-5),
+                                            ("chain_opaque_96x96", 2e-2, 5e-5)])
+def test_operator_chain_vs_reference_golden(name, gtol, itol):
+    """ProjectGaussians -> RasterizeGaussians (autograd operators) against the reference CPU back end's
+    outputs for the same inputs.  Full-chain tolerances: image 5e-5 away from
+    alpha-threshold flips; gradients rel-L2 2e-3 (projection round-off D3 feeds the rasterizer; opaque
+    case additionally has the D5 fringe)."""
+    g = load_golden(name)
+    fx, fy, cx, cy = [float(v) for v in g["intrins"]]
+    H, W = [int(v) for v in g["hw"]]
+    means, scales, quats = (cu(g[k]).requires_grad_() for k in ("means", "scales", "quats"))
+    colors, opac = cu(g["colors"]).requires_grad_(), cu(g["opacities"]).requires_grad_()
+    tb = ops.tile_bounds(W, H)
+    xys, depths, radii, conics, nth, cov3d = ops.ProjectGaussians.apply(
+        means, scales, 1.0, quats, cu(g["viewmat"]), cu(g["projmat"]), fx, fy, cx, cy, H, W, tb)
+    xys.retain_grad()  # model.cpp:171 relies on this
+    img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, colors, opac, H, W, cu(g["background"]))
+    ok, stats = image_close(npy(img), g["ref_img"], tol=itol, frac=1e-3 if gtol < 1e-2 else 1e-2)
+    assert ok, stats
+    (img * cu(g["wgt"])).sum().backward()
+    assert rel_l2(npy(xys.grad), g["ref_v_xy"]) <= gtol
+    assert rel_l2(npy(colors.grad), g["ref_v_colors"]) <= gtol
+    assert rel_l2(npy(opac.grad), g["ref_v_opacity"]) <= gtol
+    assert rel_l2(npy(means.grad), g["ref_v_means"]) <= gtol
+    assert rel_l2(npy(scales.grad), g["ref_v_scales"]) <= gtol
+    assert rel_l2(npy(quats.grad), g["ref_v_quats"]) <= gtol
+
+
+def test_sh_operator_autograd():
+    g = load_golden("sh_deg3")
+    co = cu(g["coeffs"]).requires_grad_()
+    col = ops.SphericalHarmonics.apply(2, cu(g["viewdirs"]), co)
+    (col * cu(g["wgt"])).sum().backward()
+    assert np.abs(npy(col) - g["ref_colors_d2"]).max() <= 2e-5
+    assert np.abs(npy(co.grad) - g["ref_v_coeffs_d2"]).max() <= 2e-6
+
+
+# ------------------------------------------------------------------------------------- edge cases
+def test_empty_and_fully_culled():
+    W, H = 70, 50
+    tb = ops.tile_bounds(W, H)
+    sc = _scene(64, W, H, 0.3, seed=1)
+    sc["means"][:, 2] = -20.0   # everything behind the camera -> M == 0
+    cov3d, xys, depths, radii, conics, nth = _project_gpu(sc)
+    assert int(radii.abs().sum()) == 0 and int(nth.sum()) == 0
+    colors = cu(np.full((64, 3), 0.5, np.float32)).requires_grad_()
+    opac = cu(sc["opacities"]).requires_grad_()
+    bg = cu(np.array([0.1, 0.2, 0.3], np.float32))
+    img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, colors, opac, H, W, bg)
+    assert torch.allclose(img, bg.expand(H, W, 3))
+    img.sum().backward()
+    assert float(colors.grad.abs().sum()) == 0.0
+    # n == 0 through the C ABI
+    z = torch.zeros((0, 3), device=DEV)
+    out = ops.project_gaussians_forward(z, z, 1.0, torch.zeros((0, 4), device=DEV), cu(sc["viewmat"]),
+                                        cu(sc["projmat"]), 10., 10., 5., 5., H, W, tb)
+    assert out[1].shape == (0, 2)
+
+
+def test_one_gaussian_covering_every_tile():
+    W, H = 160, 96
+    sc = _scene(3, W, H, 30.0, opacity=(0.5, 0.6), seed=2)
+    sc["means"][:, :2] = 0.0
+    colors = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    (out, fT, fI), o, st = _raster_both(sc, colors, [0, 0, 0])
+    assert st["m"] == 3 * st["tb"][0] * st["tb"][1]
+    ok, stats = image_close(npy(out), o["out_img"], tol=1e-5)
+    assert ok, stats
+
+
+# ---------------------------------------------------------------- full-size properties (config C2)
+@pytest.mark.parametrize("n,W,H,scale", [(1_000_000, 1920, 1080, 0.02)])
+def test_full_size_properties_and_oracle(n, W, H, scale):
+    sc = make_scene(n, W, H, scale=scale, sh_degree=3, opacity=(0.05, 0.95), seed=0)
+    tb = ops.tile_bounds(W, H)
+    T = tb[0] * tb[1]
+    coeffs, vd = cu(sc["coeffs"]), cu(sc["viewdirs"])
+    col = ops.compute_sh_forward(3, 3, vd, coeffs)
+    # SH is linear in the coefficients
+    col2 = ops.compute_sh_forward(3, 3, vd, coeffs * 2)
+    assert torch.equal(col2, col * 2)
+    rgbs = torch.clamp_min(col + 0.5, 0.0)
+    cov3d, xys, depths, radii, conics, nth = _project_gpu(sc)
+    o = _project_orc(sc)
+    assert np.array_equal(npy(radii), o["radii"]) and np.array_equal(npy(nth), o["num_tiles_hit"])
+    cum = ops.cumsum_tiles_hit(nth)
+    m = int(cum[-1])
+    assert m == int(o["num_tiles_hit"].astype(np.int64).sum())
+    isect, gids, ks, gs, bins, idx = ops.binAndSortGaussians(n, m, xys, depths, radii, cum, tb, return_index=True)
+    ksn, idxn, binsn = npy(ks), npy(idx), npy(bins)
+    assert np.all(np.diff(ksn) >= 0)                                   # sortedness
+    assert np.array_equal(np.sort(idxn), np.arange(m, dtype=np.int32))  # a permutation
+    assert np.array_equal(npy(isect)[idxn], ksn)                        # ... of the input keys
+    nz = binsn[:, 1] > binsn[:, 0]
+    assert (binsn[nz, 1] - binsn[nz, 0]).sum() == m                     # bins partition [0, M)
+    tiles_of_keys = (ksn >> 32).astype(np.int64)
+    assert np.array_equal(np.bincount(tiles_of_keys, minlength=T), (binsn[:, 1] - binsn[:, 0]))
+    ob = orc.bin_and_sort(o["xys"], o["depths"], o["radii"], npy(cum), H, W)
+    assert np.array_equal(ksn, ob["isect_ids_sorted"]) and np.array_equal(npy(gs), ob["gaussian_ids_sorted"])
+    assert np.array_equal(binsn, ob["tile_bins"])
+    bg = cu(np.zeros(3, np.float32))
+    opac = cu(sc["opacities"])
+    out, fT, fI, rec = ops.rasterize_forward(tb, (W, H, 1), gs, idx, bins, xys, conics, rgbs, opac, bg)
+    assert bool(torch.isfinite(out).all()) and float(out.min()) >= 0.0
+    orf = orc.rasterize_forward(H, W, npy(gs), binsn, npy(xys), npy(conics), npy(rgbs), sc["opacities"], [0, 0, 0],
+                                exp_mode=1)
+    ok, stats = image_close(npy(out), orf["out_img"], tol=2e-5, frac=1e-3)
+    assert ok, stats
+    rng = np.random.default_rng(0)
+    wgt = cu(rng.uniform(-1, 1, (H, W, 3)).astype(np.float32))
+    v = ops.rasterize_backward(H, W, n, m, bins, rec, cum, bg, fT, fI, wgt)
+    v2 = ops.rasterize_backward(H, W, n, m, bins, rec, cum, bg, fT, fI, wgt * 2)
+    for a, b in zip(v, v2):
+        assert torch.equal(a * 2, b)                                    # backward is linear in v_output
+    orb = orc.rasterize_backward(H, W, npy(gs), binsn, npy(xys), npy(conics), npy(rgbs), sc["opacities"], [0, 0, 0],
+                                 npy(fT), npy(fI), npy(wgt), exp_mode=1)
+    for a, b in zip(v, (orb["v_xy"], orb["v_conic"], orb["v_colors"], orb["v_opacity"])):
+        assert rel_l2(npy(a), b) <= 1e-3
