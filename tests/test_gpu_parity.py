@@ -52,7 +52,7 @@ def test_sh_ragged_sizes(n, deg):
     col = ops.compute_sh_forward(deg, deg, cu(vd), cu(co))
     assert np.abs(npy(col) - orc.sh_forward(deg, vd, co)).max() <= 1e-5
     vc = ops.compute_sh_backward(deg, deg, cu(vd), cu(vcol))
-    assert np.abs(npy(vc) - orc.sh_backward(deg, K, vd, vcol)).max() <= 1e-6
+    assert np.abs(npy(vc) - orc.sh_backward(deg, K, vd, vcol)).max() <= 3e-6
 
 
 # ------------------------------------------------------------------------------- projection + bins
