@@ -57,13 +57,14 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
     const float px = (float)X;
     const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
 
-    float T[RK_PIX], bufr[RK_PIX], bufg[RK_PIX], bufb[RK_PIX];
+    float T[RK_PIX], bufr[RK_PIX], bufg[RK_PIX], bufb[RK_PIX], py[RK_PIX];
     float vor[RK_PIX], vog[RK_PIX], vob[RK_PIX], q[RK_PIX];
     int binf[RK_PIX];
     int my_max = -1;
 #pragma unroll
     for (int j = 0; j < RK_PIX; ++j) {
         const int Y = Y0 + 2 * j;
+        py[j] = (float)Y;
         bufr[j] = bufg[j] = bufb[j] = 0.f;
         if (X < img_w && Y < img_h) {
             const size_t p = (size_t)Y * img_w + X;
@@ -120,19 +121,20 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
             const float4 q1 = ring.rec[s][t].q1;
             const float4 q2 = ring.rec[s][t].q2;
             const float dx = q0.x - px;
-            const float adx2 = q1.x * dx * dx;
+            const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
             const float bdx = q1.y * dx;
+            const float ca = 2.f * q1.x, cc = 2.f * q1.z;  // conic a, c
             float a_x = 0.f, a_y = 0.f, a_ca = 0.f, a_cb = 0.f, a_cc = 0.f;
             float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_o = 0.f;
             bool any = false;
 #pragma unroll
             for (int j = 0; j < RK_PIX; ++j) {
-                const float dy = q0.y - (float)(Y0 + 2 * j);
-                const float sigma = 0.5f * (adx2 + q1.z * dy * dy) + bdx * dy;
-                const float vis = __expf(-sigma);
+                const float dy = q0.y - py[j];
+                const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
+                if (__float_as_uint(sigma) > __float_as_uint(q1.w)) continue;  // !(0 <= sigma <= smax), no exp
+                const float vis = ex2_approx(sigma * -1.4426950408889634f);
                 const float alpha = fminf(0.99f, q0.z * vis);
-                const bool valid = (idx <= binf[j]) && !(sigma < 0.f || alpha < (1.f / 255.f));
-                if (valid) {
+                if (idx <= binf[j] && alpha >= (1.f / 255.f)) {
                     any = true;
                     const float ra = rcp_approx(1.f - alpha);
                     T[j] *= ra;
@@ -152,8 +154,8 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                     a_ca += hv * dx * dx;
                     a_cb += hv * dx * dy;
                     a_cc += hv * dy * dy;
-                    a_x += v_sigma * (q1.x * dx + q1.y * dy);
-                    a_y += v_sigma * (q1.y * dx + q1.z * dy);
+                    a_x += v_sigma * (ca * dx + q1.y * dy);
+                    a_y += v_sigma * (q1.y * dx + cc * dy);
                     a_o += vis * v_alpha;
                 }
             }

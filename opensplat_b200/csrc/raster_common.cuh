@@ -6,8 +6,10 @@
 // tile's whole list is ONE contiguous range that the blend kernels pull with 1-D TMA bulk copies.
 //   q0 = { x, y, opacity, bits(k) }   k = slot of this intersection in the UNSORTED (Gaussian-major)
 //                                      order, i.e. cum_tiles_hit[g-1] + position inside g's tile bbox
-//   q1 = { conic a, b, c, bits(g) }   g = Gaussian id
-//   q2 = { r, g, b, 0 }
+//   q1 = { a/2, b, c/2, smax }        conic with the 1/2 of sigma folded in; smax = ln(255*opacity) + 1e-3
+//                                      is a CONSERVATIVE bound: sigma > smax  =>  alpha < 1/255, so the
+//                                      blend loops reject most (pixel, Gaussian) pairs before the exp
+//   q2 = { r, g, b, bits(g) }         g = Gaussian id (debug / tooling only)
 struct __align__(16) GsbRecord {
     float4 q0, q1, q2;
 };

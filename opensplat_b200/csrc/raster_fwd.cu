@@ -30,10 +30,15 @@ pack_records_kernel(int m, const int *__restrict__ gaussian_ids_sorted,
     const int k = sorted_index ? sorted_index[i] : i;
     const float2 xy = __ldg(xys + g);
     GsbRecord r;
-    r.q0 = make_float4(xy.x, xy.y, __ldg(opacities + g), __int_as_float(k));
-    r.q1 = make_float4(__ldg(conics + 3 * g), __ldg(conics + 3 * g + 1), __ldg(conics + 3 * g + 2),
+    const float opac = __ldg(opacities + g);
+    // alpha >= 1/255  <=>  sigma <= ln(255 * opac); +1e-3 keeps the pre-test conservative w.r.t. the
+    // rounding of sigma and of ex2.approx (the exact alpha test still runs inside the branch)
+    const float smax = fmaxf(0.f, __logf(255.f * fmaxf(opac, 1e-30f)) + 1e-3f);  // >= +0: compared as unsigned bits
+    r.q0 = make_float4(xy.x, xy.y, opac, __int_as_float(k));
+    r.q1 = make_float4(0.5f * __ldg(conics + 3 * g), __ldg(conics + 3 * g + 1), 0.5f * __ldg(conics + 3 * g + 2),
+                       smax);
+    r.q2 = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2),
                        __int_as_float(g));
-    r.q2 = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), 0.f);
     float4 *dst = reinterpret_cast<float4 *>(records + i);
     stg_stream4(dst, r.q0);
     stg_stream4(dst + 1, r.q1);
@@ -70,13 +75,17 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
     const int L = range.y - range.x;
     const int nchunks = (L + RK_CHUNK - 1) / RK_CHUNK;
 
-    float T[RK_PIX], cr[RK_PIX], cg[RK_PIX], cb[RK_PIX];
+    // T[j] > 0: transmittance of a live pixel.  A finished pixel keeps its final transmittance NEGATED
+    // (sign bit == "done"), so the hot loop needs no separate done test: T*(1-alpha) <= 1e-4 sends it
+    // to the (rare) terminate branch, which ignores pixels that are already negative.
+    float T[RK_PIX], cr[RK_PIX], cg[RK_PIX], cb[RK_PIX], py[RK_PIX];
     int last[RK_PIX];
     unsigned done = 0;  // bit j: pixel j finished (or outside the image)
 #pragma unroll
     for (int j = 0; j < RK_PIX; ++j) {
         T[j] = 1.f; cr[j] = cg[j] = cb[j] = 0.f; last[j] = 0;
-        if (X >= img_w || Y0 + 2 * j >= img_h) done |= 1u << j;
+        py[j] = (float)(Y0 + 2 * j);
+        if (X >= img_w || Y0 + 2 * j >= img_h) { done |= 1u << j; T[j] = -1.f; }
     }
 
     auto issue = [&](int c) {
@@ -104,25 +113,27 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
             const float4 q1 = ring.rec[s][t].q1;
             const float4 q2 = ring.rec[s][t].q2;
             const float dx = q0.x - px;
-            const float adx2 = q1.x * dx * dx;
+            const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
             const float bdx = q1.y * dx;
 #pragma unroll
             for (int j = 0; j < RK_PIX; ++j) {
-                const float dy = q0.y - (float)(Y0 + 2 * j);
-                const float sigma = 0.5f * (adx2 + q1.z * dy * dy) + bdx * dy;
-                const float alpha = fminf(0.999f, q0.z * __expf(-sigma));
-                const bool live = !((done >> j) & 1u) && !(sigma < 0.f || alpha < (1.f / 255.f));
-                if (live) {
-                    const float next_T = T[j] * (1.f - alpha);
-                    if (next_T <= 1e-4f) {
-                        done |= 1u << j;
-                    } else {
-                        const float vis = alpha * T[j];
-                        cr[j] += q2.x * vis;
-                        cg[j] += q2.y * vis;
-                        cb[j] += q2.z * vis;
-                        T[j] = next_T;
-                        last[j] = idx0 + t;
+                const float dy = q0.y - py[j];
+                // sigma = (a/2)dx^2 + (c/2)dy^2 + b dx dy   (forward.cu:340-342)
+                const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
+                if (__float_as_uint(sigma) <= __float_as_uint(q1.w)) {     // 0 <= sigma <= smax in ONE compare, no exp
+                    const float alpha = fminf(0.999f, q0.z * ex2_approx(sigma * -1.4426950408889634f));
+                    if (alpha >= (1.f / 255.f)) {
+                        const float next_T = T[j] * (1.f - alpha);
+                        if (next_T <= 1e-4f) {                          // terminate BEFORE blending
+                            if (T[j] > 0.f) { T[j] = -T[j]; done |= 1u << j; }
+                        } else {
+                            const float vis = alpha * T[j];
+                            cr[j] = fmaf(q2.x, vis, cr[j]);
+                            cg[j] = fmaf(q2.y, vis, cg[j]);
+                            cb[j] = fmaf(q2.z, vis, cb[j]);
+                            T[j] = next_T;
+                            last[j] = idx0 + t;
+                        }
                     }
                 }
             }
@@ -140,11 +151,12 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         const int Y = Y0 + 2 * j;
         if (X < img_w && Y < img_h) {
             const size_t p = (size_t)Y * img_w + X;
-            final_Ts[p] = T[j];
+            const float Tf = fabsf(T[j]);
+            final_Ts[p] = Tf;
             final_idx[p] = last[j];
-            out_img[3 * p] = cr[j] + T[j] * bg0;
-            out_img[3 * p + 1] = cg[j] + T[j] * bg1;
-            out_img[3 * p + 2] = cb[j] + T[j] * bg2;
+            out_img[3 * p] = cr[j] + Tf * bg0;
+            out_img[3 * p + 1] = cg[j] + Tf * bg1;
+            out_img[3 * p + 2] = cb[j] + Tf * bg2;
         }
     }
 }
