@@ -115,12 +115,13 @@ int gsb_gather_bin_edges(int m, int num_tiles, const int64_t *isect_ids_sorted,
  *   [tiles,2], xys [n,2], conics [n,3], colors [n,3], opacities [n], background [3] on device) plus
  *   sorted_index [m] (the permutation from gsb_sort_intersects: sorted position -> unsorted
  *   intersection slot).  `records` is a caller-provided buffer of gsb_raster_records_bytes(m): the
- *   call packs the depth-sorted per-intersection stream (48 B/intersection) that the blend kernel
- *   pulls with TMA bulk copies; keep it for the backward pass.  Outputs out_img [H,W,3],
+ *   call packs the depth-sorted per-intersection stream (48 B/intersection + 256 B of scratch) that the
+ *   blend kernel pulls with TMA bulk copies; keep it for the backward pass.  Outputs out_img [H,W,3],
  *   final_Ts [H,W], final_idx [H,W] i32, fully written.
  * gsb_rasterize_backward replaces rasterize_backward_tensor (bindings.h:174-189,
- *   bindings.cu:569-632, kernel backward.cu:161-355).  Consumes `records` from the forward call,
- *   cum_tiles_hit [n] (gsb_cumsum_tiles_hit) and a scratch buffer grad_rows of
+ *   bindings.cu:569-632, kernel backward.cu:161-355).  Consumes `records` from the forward call (its
+ *   trailing scratch words are rewritten, hence non-const), conics [n,3] and opacities [n] (as the
+ *   reference's signature), cum_tiles_hit [n] (gsb_cumsum_tiles_hit) and a scratch buffer grad_rows of
  *   gsb_raster_grad_rows_bytes(m).  v_output [H,W,3]; v_output_alpha [H,W] may be NULL (== zeros,
  *   rasterize_gaussians.cpp:108).  Writes v_xy [n,2], v_conic [n,3], v_colors [n,3], v_opacity [n]
  *   completely (no atomics, bit-reproducible run to run). */
@@ -133,8 +134,8 @@ int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tiles_y, int m,
                           void *records, float *out_img, float *final_Ts, int32_t *final_idx,
                           gsb_stream_t stream);
 int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
-                           const int32_t *tile_bins, const void *records,
-                           const int32_t *cum_tiles_hit, const float *background,
+                           const int32_t *tile_bins, const float *conics, const float *opacities,
+                           void *records, const int32_t *cum_tiles_hit, const float *background,
                            const float *final_Ts, const int32_t *final_idx, const float *v_output,
                            const float *v_output_alpha, void *grad_rows, float *v_xy, float *v_conic,
                            float *v_colors, float *v_opacity, gsb_stream_t stream);

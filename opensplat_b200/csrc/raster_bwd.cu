@@ -11,19 +11,20 @@
 //  * one warp owns a whole 16x16 tile with 8 pixels per lane, so the 256 per-pixel contributions to a
 //    Gaussian are first summed over 8 pixels in registers and then across the 32 lanes ONCE per
 //    (tile, Gaussian) with a halving butterfly (14 shuffles instead of the reference's 8 warps x 45);
+//  * per pixel only 3 moments of w = alpha_unclamped * v_alpha are accumulated (sum w, sum w dy,
+//    sum w dy^2) plus the colour gradient; the x-moments follow per lane (dx is a lane constant) and
+//    the linear map moments -> (v_xy, v_conic, v_opacity) is applied once per GAUSSIAN afterwards;
 //  * the per-(tile, Gaussian) partial goes to a private 48-B row of `grad_rows`, indexed by the
 //    intersection's slot k in the Gaussian-major (unsorted) order -- plain stores, no atomics;
 //  * a second kernel sums each Gaussian's contiguous rows [cum[g-1], cum[g]) in a fixed order and
 //    writes v_xy / v_conic / v_colors / v_opacity once.  Results are bit-reproducible run to run.
-// Records are streamed back-to-front with the same per-warp TMA bulk-copy ring as the forward pass.
+// Records are streamed back-to-front with the same per-warp TMA bulk-copy ring, persistent tile
+// scheduling and two-level culling as the forward pass.
 #include "raster_common.cuh"
 
-namespace {
+int gsb_blend_grid(const void *kernel, int num_tiles);
 
-struct __align__(128) WarpRingB {
-    GsbRecord rec[RK_STAGES][RK_CHUNK];
-    uint64_t full[RK_STAGES];
-};
+namespace {
 
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
@@ -31,180 +32,208 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ void zero_row(float *grad_rows, int k) {
+    float4 *row = reinterpret_cast<float4 *>(grad_rows + (size_t)k * GSB_GRAD_ROW_FLOATS);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    row[0] = z; row[1] = z; row[2] = z;
+}
+
 __global__ void __launch_bounds__(RK_THREADS)
 rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                           const int2 *__restrict__ tile_bins, const GsbRecord *__restrict__ records,
                           const float *__restrict__ background, const float *__restrict__ final_Ts,
                           const int *__restrict__ final_idx, const float *__restrict__ v_output,
-                          const float *__restrict__ v_output_alpha, float *__restrict__ grad_rows) {
-    __shared__ WarpRingB rings[RK_WARPS];
+                          const float *__restrict__ v_output_alpha, float *__restrict__ grad_rows,
+                          unsigned *__restrict__ tile_counter) {
+    __shared__ WarpRing rings[RK_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * RK_WARPS + warp;
-    if (tile >= num_tiles) return;
-    const int2 range = tile_bins[tile];
-    if (range.y <= range.x) return;
-    WarpRingB &ring = rings[warp];
+    WarpRing &ring = rings[warp];
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < RK_STAGES; ++s) mbar_init(&ring.full[s], 1);
         mbar_fence_init();
     }
     __syncwarp();
-
-    const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int X = tx * GSB_TILE + (lane & 15);
-    const int Y0 = ty * GSB_TILE + (lane >> 4);
-    const float px = (float)X;
     const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+    unsigned gchunk = 0;
 
-    float T[RK_PIX], bufr[RK_PIX], bufg[RK_PIX], bufb[RK_PIX], py[RK_PIX];
-    float vor[RK_PIX], vog[RK_PIX], vob[RK_PIX], q[RK_PIX];
-    int binf[RK_PIX];
-    int my_max = -1;
+    while (true) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= num_tiles) break;
+        const int2 range = tile_bins[tile];
+        if (range.y <= range.x) continue;
+
+        const int tx = tile % tiles_x, ty = tile / tiles_x;
+        const int X = tx * GSB_TILE + (lane & 15);
+        const int Y0 = ty * GSB_TILE + (lane >> 4);
+        const float px = (float)X;
+        const float tile_x0 = (float)(tx * GSB_TILE), tile_y0 = (float)(ty * GSB_TILE);
+
+        float T[RK_PIX], bufr[RK_PIX], bufg[RK_PIX], bufb[RK_PIX], py[RK_PIX];
+        float vor[RK_PIX], vog[RK_PIX], vob[RK_PIX], q[RK_PIX];
+        int binf[RK_PIX];
+        int my_max = -1;
 #pragma unroll
-    for (int j = 0; j < RK_PIX; ++j) {
-        const int Y = Y0 + 2 * j;
-        py[j] = (float)Y;
-        bufr[j] = bufg[j] = bufb[j] = 0.f;
-        if (X < img_w && Y < img_h) {
-            const size_t p = (size_t)Y * img_w + X;
-            const float Tf = final_Ts[p];
-            T[j] = Tf;
-            vor[j] = v_output[3 * p]; vog[j] = v_output[3 * p + 1]; vob[j] = v_output[3 * p + 2];
-            const float voa = v_output_alpha ? v_output_alpha[p] : 0.f;
-            // backward.cu:313-317: T_final*ra*v_out_alpha - T_final*ra*(bg . v_out)  ==  ra * q
-            q[j] = Tf * (voa - (bg0 * vor[j] + bg1 * vog[j] + bg2 * vob[j]));
-            binf[j] = final_idx[p];
-        } else {
-            T[j] = 1.f; vor[j] = vog[j] = vob[j] = 0.f; q[j] = 0.f;
-            binf[j] = -1;  // never valid
+        for (int j = 0; j < RK_PIX; ++j) {
+            const int Y = Y0 + 2 * j;
+            py[j] = (float)Y;
+            bufr[j] = bufg[j] = bufb[j] = 0.f;
+            if (X < img_w && Y < img_h) {
+                const size_t p = (size_t)Y * img_w + X;
+                const float Tf = final_Ts[p];
+                T[j] = Tf;
+                vor[j] = v_output[3 * p]; vog[j] = v_output[3 * p + 1]; vob[j] = v_output[3 * p + 2];
+                const float voa = v_output_alpha ? v_output_alpha[p] : 0.f;
+                // backward.cu:313-317: T_final*ra*v_out_alpha - T_final*ra*(bg . v_out)  ==  ra * q
+                q[j] = Tf * (voa - (bg0 * vor[j] + bg1 * vog[j] + bg2 * vob[j]));
+                binf[j] = final_idx[p];
+            } else {
+                T[j] = 1.f; vor[j] = vog[j] = vob[j] = 0.f; q[j] = 0.f;
+                binf[j] = -1;  // never valid
+            }
+            my_max = max(my_max, binf[j]);
         }
-        my_max = max(my_max, binf[j]);
-    }
-    const int warp_max = __reduce_max_sync(0xffffffffu, my_max);
-    const int hi = min(range.y - 1, warp_max);  // last sorted index any pixel of this tile blended
+        const int warp_max = __reduce_max_sync(0xffffffffu, my_max);
+        const int hi = min(range.y - 1, warp_max);  // last sorted index any pixel of this tile blended
 
-    // intersections behind every pixel's last contributor: zero rows
-    for (int idx = hi + 1 + lane; idx < range.y; idx += 32) {
-        const int k = __float_as_int(__ldg(&records[idx].q0.w));
-        float4 *row = reinterpret_cast<float4 *>(grad_rows + (size_t)k * GSB_GRAD_ROW_FLOATS);
-        row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        row[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const int L = hi - range.x + 1;
-    if (L <= 0) return;
-    const int nchunks = (L + RK_CHUNK - 1) / RK_CHUNK;
+        // intersections behind every pixel's last contributor: zero rows
+        for (int idx = hi + 1 + lane; idx < range.y; idx += 32)
+            zero_row(grad_rows, __float_as_int(__ldg(&records[idx].q0.w)));
+        const int L = hi - range.x + 1;
+        if (L <= 0) continue;
+        const int nchunks = (L + RK_CHUNK - 1) / RK_CHUNK;
 
-    // chunk c (c = 0 is the farthest) covers sorted indices [lo_c, lo_c + cnt_c)
-    auto chunk_lo = [&](int c) { return max(range.x, hi + 1 - (c + 1) * RK_CHUNK); };
-    auto chunk_cnt = [&](int c) { return (hi + 1 - c * RK_CHUNK) - chunk_lo(c); };
-    auto issue = [&](int c) {
-        if (lane == 0) {
-            const int s = c % RK_STAGES;
-            const uint32_t bytes = (uint32_t)chunk_cnt(c) * (uint32_t)sizeof(GsbRecord);
-            mbar_arrive_expect_tx(&ring.full[s], bytes);
-            tma_load_1d(&ring.rec[s][0], records + chunk_lo(c), bytes, &ring.full[s]);
-        }
-    };
-    const int pro = min(RK_STAGES, nchunks);
-    for (int c = 0; c < pro; ++c) issue(c);
-    int issued = pro;
+        // chunk c (c = 0 is the farthest) covers sorted indices [lo_c, lo_c + cnt_c)
+        const unsigned g0 = gchunk;
+        auto stage_of = [&](int c) { return (g0 + (unsigned)c) % RK_STAGES; };
+        auto parity_of = [&](int c) { return ((g0 + (unsigned)c) / RK_STAGES) & 1u; };
+        auto chunk_lo = [&](int c) { return max(range.x, hi + 1 - (c + 1) * RK_CHUNK); };
+        auto chunk_cnt = [&](int c) { return (hi + 1 - c * RK_CHUNK) - chunk_lo(c); };
+        auto issue = [&](int c) {
+            if (lane == 0) {
+                const unsigned s = stage_of(c);
+                const uint32_t bytes = (uint32_t)chunk_cnt(c) * (uint32_t)sizeof(GsbRecord);
+                mbar_arrive_expect_tx(&ring.full[s], bytes);
+                tma_load_1d(&ring.rec[s][0], records + chunk_lo(c), bytes, &ring.full[s]);
+            }
+        };
+        const int pro = min(RK_STAGES, nchunks);
+        for (int c = 0; c < pro; ++c) issue(c);
+        int issued = pro;
 
-    for (int c = 0; c < nchunks; ++c) {
-        const int s = c % RK_STAGES;
-        mbar_wait(&ring.full[s], (uint32_t)(c / RK_STAGES) & 1u);
-        const int lo = chunk_lo(c), cnt = chunk_cnt(c);
-        for (int t = cnt - 1; t >= 0; --t) {
-            const int idx = lo + t;
-            const float4 q0 = ring.rec[s][t].q0;
-            const float4 q1 = ring.rec[s][t].q1;
-            const float4 q2 = ring.rec[s][t].q2;
-            const float dx = q0.x - px;
-            const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
-            const float bdx = q1.y * dx;
-            const float ca = 2.f * q1.x, cc = 2.f * q1.z;  // conic a, c
-            float a_x = 0.f, a_y = 0.f, a_ca = 0.f, a_cb = 0.f, a_cc = 0.f;
-            float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_o = 0.f;
-            bool any = false;
+        for (int c = 0; c < nchunks; ++c) {
+            const unsigned s = stage_of(c);
+            mbar_wait(&ring.full[s], parity_of(c));
+            const int lo = chunk_lo(c), cnt = chunk_cnt(c);
+            // level-1 cull: lane l tests record l; culled records get their zero row right here
+            unsigned my_mask = 0;
+            if (lane < cnt) {
+                my_mask = record_slot_mask(ring.rec[s][lane], tile_x0, tile_y0);
+                if (my_mask == 0u) zero_row(grad_rows, __float_as_int(ring.rec[s][lane].q0.w));
+            }
+            unsigned live = __ballot_sync(0xffffffffu, my_mask != 0u);
+            while (live) {
+                const int t = 31 - __clz(live);        // back to front
+                live &= ~(1u << t);
+                const unsigned rm = __shfl_sync(0xffffffffu, my_mask, t);
+                const int idx = lo + t;
+                const float4 q0 = ring.rec[s][t].q0;
+                const float4 q1 = ring.rec[s][t].q1;
+                const float4 q2 = ring.rec[s][t].q2;
+                const float smax = fmaxf(0.f, fmaf(q0.z, GSB_LN2, GSB_SMAX_BIAS));
+                const float dx = q0.x - px;
+                const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
+                const float bdx = q1.y * dx;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f;  // sum w, sum w dy, sum w dy^2 over this lane's pixels
+                float a_r = 0.f, a_g = 0.f, a_b = 0.f;
+                bool any = false;
 #pragma unroll
-            for (int j = 0; j < RK_PIX; ++j) {
-                const float dy = q0.y - py[j];
-                const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
-                if (__float_as_uint(sigma) > __float_as_uint(q1.w)) continue;  // !(0 <= sigma <= smax), no exp
-                const float vis = ex2_approx(sigma * -1.4426950408889634f);
-                const float alpha = fminf(0.99f, q0.z * vis);
-                if (idx <= binf[j] && alpha >= (1.f / 255.f)) {
-                    any = true;
-                    const float ra = rcp_approx(1.f - alpha);
-                    T[j] *= ra;
-                    const float fac = alpha * T[j];
-                    a_r += fac * vor[j];
-                    a_g += fac * vog[j];
-                    a_b += fac * vob[j];
-                    float v_alpha = (q2.x * T[j] - bufr[j] * ra) * vor[j];
-                    v_alpha += (q2.y * T[j] - bufg[j] * ra) * vog[j];
-                    v_alpha += (q2.z * T[j] - bufb[j] * ra) * vob[j];
-                    v_alpha += ra * q[j];
-                    bufr[j] += q2.x * fac;
-                    bufg[j] += q2.y * fac;
-                    bufb[j] += q2.z * fac;
-                    const float v_sigma = -q0.z * vis * v_alpha;
-                    const float hv = 0.5f * v_sigma;
-                    a_ca += hv * dx * dx;
-                    a_cb += hv * dx * dy;
-                    a_cc += hv * dy * dy;
-                    a_x += v_sigma * (ca * dx + q1.y * dy);
-                    a_y += v_sigma * (q1.y * dx + cc * dy);
-                    a_o += vis * v_alpha;
+                for (int j = 0; j < RK_PIX; ++j) {
+                    if (!((rm >> j) & 1u)) continue;                          // warp-uniform
+                    const float dy = q0.y - py[j];
+                    const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
+                    if (__float_as_uint(sigma) > __float_as_uint(smax)) continue;  // !(0 <= sigma <= smax)
+                    const float au = ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z));   // opac * exp(-sigma)
+                    const float alpha = fminf(0.99f, au);
+                    if (idx <= binf[j] && alpha >= (1.f / 255.f)) {
+                        any = true;
+                        const float ra = rcp_approx(1.f - alpha);
+                        T[j] *= ra;
+                        const float fac = alpha * T[j];
+                        a_r = fmaf(fac, vor[j], a_r);
+                        a_g = fmaf(fac, vog[j], a_g);
+                        a_b = fmaf(fac, vob[j], a_b);
+                        float v_alpha = (q2.x * T[j] - bufr[j] * ra) * vor[j];
+                        v_alpha = fmaf(q2.y * T[j] - bufg[j] * ra, vog[j], v_alpha);
+                        v_alpha = fmaf(q2.z * T[j] - bufb[j] * ra, vob[j], v_alpha);
+                        v_alpha = fmaf(ra, q[j], v_alpha);
+                        bufr[j] = fmaf(q2.x, fac, bufr[j]);
+                        bufg[j] = fmaf(q2.y, fac, bufg[j]);
+                        bufb[j] = fmaf(q2.z, fac, bufb[j]);
+                        // v_sigma = -opac*vis*v_alpha = -w (backward.cu:323); v_opacity += vis*v_alpha = w/opac
+                        const float w = au * v_alpha;
+                        const float wdy = w * dy;
+                        s0 += w;
+                        s1 += wdy;
+                        s2 = fmaf(wdy, dy, s2);
+                    }
                 }
-            }
-            const int k = __float_as_int(q0.w);
-            float *row = grad_rows + (size_t)k * GSB_GRAD_ROW_FLOATS;
-            if (!__any_sync(0xffffffffu, any)) {
-                if (lane < 9) row[lane] = 0.f;
-                continue;
-            }
-            // ---- one cross-lane reduction per (tile, Gaussian): 8 values by halving, 1 by butterfly ----
-            float v0 = a_x, v1 = a_y, v2 = a_ca, v3 = a_cb, v4 = a_cc, v5 = a_r, v6 = a_g, v7 = a_b;
-            {
-                const bool up = lane & 16;
-                float s0 = up ? v0 : v4, s1 = up ? v1 : v5, s2 = up ? v2 : v6, s3 = up ? v3 : v7;
-                float k0 = up ? v4 : v0, k1 = up ? v5 : v1, k2 = up ? v6 : v2, k3 = up ? v7 : v3;
-                v0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
-                v1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-                v2 = k2 + __shfl_xor_sync(0xffffffffu, s2, 16);
-                v3 = k3 + __shfl_xor_sync(0xffffffffu, s3, 16);
-            }
-            {
-                const bool up = lane & 8;
-                float s0 = up ? v0 : v2, s1 = up ? v1 : v3;
-                float k0 = up ? v2 : v0, k1 = up ? v3 : v1;
-                v0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
-                v1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
-            }
-            {
-                const bool up = lane & 4;
-                float s0 = up ? v0 : v1;
-                float k0 = up ? v1 : v0;
-                v0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
-            }
-            v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
-            v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+                const int k = __float_as_int(q0.w);
+                float *row = grad_rows + (size_t)k * GSB_GRAD_ROW_FLOATS;
+                if (!__any_sync(0xffffffffu, any)) {
+                    if (lane < 9) row[lane] = 0.f;
+                    continue;
+                }
+                // ---- one cross-lane reduction per (tile, Gaussian): 8 values by halving, 1 by butterfly
+                const float sx = dx * s0;
+                float v0 = s0, v1 = sx, v2 = s1, v3 = dx * sx, v4 = dx * s1, v5 = s2, v6 = a_r, v7 = a_g;
+                float v8 = a_b;
+                {
+                    const bool up = lane & 16;
+                    const float t0 = up ? v0 : v4, t1 = up ? v1 : v5, t2 = up ? v2 : v6, t3 = up ? v3 : v7;
+                    const float k0 = up ? v4 : v0, k1 = up ? v5 : v1, k2 = up ? v6 : v2, k3 = up ? v7 : v3;
+                    v0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 16);
+                    v1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 16);
+                    v2 = k2 + __shfl_xor_sync(0xffffffffu, t2, 16);
+                    v3 = k3 + __shfl_xor_sync(0xffffffffu, t3, 16);
+                }
+                {
+                    const bool up = lane & 8;
+                    const float t0 = up ? v0 : v2, t1 = up ? v1 : v3;
+                    const float k0 = up ? v2 : v0, k1 = up ? v3 : v1;
+                    v0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 8);
+                    v1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 8);
+                }
+                {
+                    const bool up = lane & 4;
+                    const float t0 = up ? v0 : v1;
+                    const float k0 = up ? v1 : v0;
+                    v0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 4);
+                }
+                v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+                v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a_o += __shfl_xor_sync(0xffffffffu, a_o, o);
-            // lane l now holds the total of value (l >> 2); lane 1 additionally stores v_opacity
-            const bool w8 = (lane == 1);
-            if (((lane & 3) == 0) || w8) row[w8 ? 8 : (lane >> 2)] = w8 ? a_o : v0;
+                for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
+                // lane l now holds the total of value (l >> 2); lane 1 additionally stores value 8
+                const bool w8 = (lane == 1);
+                if (((lane & 3) == 0) || w8) row[w8 ? 8 : (lane >> 2)] = w8 ? v8 : v0;
+            }
+            __syncwarp();
+            if (issued < nchunks) { issue(issued); ++issued; }
         }
+        gchunk = g0 + (unsigned)issued;
         __syncwarp();
-        if (issued < nchunks) { issue(issued); ++issued; }
     }
 }
 
-// Sum each Gaussian's rows (contiguous in the unsorted order) and write the four gradient tensors.
+// Sum each Gaussian's rows (contiguous in the unsorted order), apply the moment -> gradient map
+// (backward.cu:323-329 restated on sums) and write the four gradient tensors:
+//   v_sigma = -w:  v_conic = -1/2 (Sxx, Sxy, Syy),  v_xy = -(a Sx + b Sy, b Sx + c Sy),  v_opacity = S0/opac
 __global__ void __launch_bounds__(256)
 reduce_grad_rows_kernel(int n, const int *__restrict__ cum_tiles_hit, const float *__restrict__ grad_rows,
+                        const float *__restrict__ conics, const float *__restrict__ opacities,
                         float2 *__restrict__ v_xy, float *__restrict__ v_conic,
                         float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,10 +248,13 @@ reduce_grad_rows_kernel(int n, const int *__restrict__ cum_tiles_hit, const floa
         a[4] += r1.x; a[5] += r1.y; a[6] += r1.z; a[7] += r1.w;
         a[8] += r8;
     }
-    v_xy[g] = make_float2(a[0], a[1]);
-    v_conic[3 * g] = a[2]; v_conic[3 * g + 1] = a[3]; v_conic[3 * g + 2] = a[4];
-    v_colors[3 * g] = a[5]; v_colors[3 * g + 1] = a[6]; v_colors[3 * g + 2] = a[7];
-    v_opacity[g] = a[8];
+    const float S0 = a[0], Sx = a[1], Sy = a[2], Sxx = a[3], Sxy = a[4], Syy = a[5];
+    const float ca = conics[3 * g], cb = conics[3 * g + 1], cc = conics[3 * g + 2];
+    const float op = opacities[g];
+    v_xy[g] = make_float2(-(ca * Sx + cb * Sy), -(cb * Sx + cc * Sy));
+    v_conic[3 * g] = -0.5f * Sxx; v_conic[3 * g + 1] = -0.5f * Sxy; v_conic[3 * g + 2] = -0.5f * Syy;
+    v_colors[3 * g] = a[6]; v_colors[3 * g + 1] = a[7]; v_colors[3 * g + 2] = a[8];
+    v_opacity[g] = (op > 0.f) ? S0 / op : 0.f;
 }
 
 }  // namespace
@@ -232,7 +264,8 @@ extern "C" size_t gsb_raster_grad_rows_bytes(int m) {
 }
 
 extern "C" int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
-                                      const int32_t *tile_bins, const void *records,
+                                      const int32_t *tile_bins, const float *conics,
+                                      const float *opacities, void *records,
                                       const int32_t *cum_tiles_hit, const float *background,
                                       const float *final_Ts, const int32_t *final_idx,
                                       const float *v_output, const float *v_output_alpha,
@@ -241,21 +274,25 @@ extern "C" int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int til
     GSB_CHECK_ARG(img_h > 0 && img_w > 0 && n >= 0 && m >= 0);
     GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
     if (n == 0) return 0;
-    GSB_CHECK_ARG(tile_bins && cum_tiles_hit && background && final_Ts && final_idx && v_output && v_xy &&
-                  v_conic && v_colors && v_opacity);
+    GSB_CHECK_ARG(tile_bins && conics && opacities && cum_tiles_hit && background && final_Ts && final_idx &&
+                  v_output && v_xy && v_conic && v_colors && v_opacity);
     GSB_CHECK_ARG(((uintptr_t)v_xy % 8) == 0);
     cudaStream_t s = (cudaStream_t)stream;
     if (m > 0) {
         GSB_CHECK_ARG(records && grad_rows && ((uintptr_t)records % 16) == 0 && ((uintptr_t)grad_rows % 16) == 0);
+        unsigned *counters = reinterpret_cast<unsigned *>(
+            reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
+        GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
         const int num_tiles = tiles_x * tiles_y;
-        rasterize_backward_kernel<<<gsb_div_up(num_tiles, RK_WARPS), RK_THREADS, 0, s>>>(
+        const int grid = gsb_blend_grid((const void *)rasterize_backward_kernel, num_tiles);
+        rasterize_backward_kernel<<<grid, RK_THREADS, 0, s>>>(
             img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
             reinterpret_cast<const GsbRecord *>(records), background, final_Ts, final_idx, v_output,
-            v_output_alpha, reinterpret_cast<float *>(grad_rows));
+            v_output_alpha, reinterpret_cast<float *>(grad_rows), counters);
     }
     reduce_grad_rows_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(
-        n, cum_tiles_hit, reinterpret_cast<const float *>(grad_rows), reinterpret_cast<float2 *>(v_xy), v_conic,
-        v_colors, v_opacity);
+        n, cum_tiles_hit, reinterpret_cast<const float *>(grad_rows), conics, opacities,
+        reinterpret_cast<float2 *>(v_xy), v_conic, v_colors, v_opacity);
     GSB_LAUNCH_CHECK();
     return 0;
 }

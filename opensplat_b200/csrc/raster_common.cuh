@@ -1,28 +1,63 @@
-// raster_common.cuh -- record stream layout and tile/pixel mapping shared by the blend kernels.
+// raster_common.cuh -- record stream layout, per-warp TMA ring and tile/pixel mapping shared by the
+// blend kernels (raster_fwd.cu, raster_bwd.cu).
 #pragma once
 #include "gsb_common.cuh"
 
 // One depth-sorted intersection = 48 bytes = three 16-byte quads, contiguous per tile, so that a
 // tile's whole list is ONE contiguous range that the blend kernels pull with 1-D TMA bulk copies.
-//   q0 = { x, y, opacity, bits(k) }   k = slot of this intersection in the UNSORTED (Gaussian-major)
-//                                      order, i.e. cum_tiles_hit[g-1] + position inside g's tile bbox
-//   q1 = { a/2, b, c/2, smax }        conic with the 1/2 of sigma folded in; smax = ln(255*opacity) + 1e-3
-//                                      is a CONSERVATIVE bound: sigma > smax  =>  alpha < 1/255, so the
-//                                      blend loops reject most (pixel, Gaussian) pairs before the exp
-//   q2 = { r, g, b, bits(g) }         g = Gaussian id (debug / tooling only)
+//   q0 = { x, y, log2(opacity), bits(k) }  k = slot of this intersection in the UNSORTED
+//                                          (Gaussian-major) order = cum_tiles_hit[g-1] + position in
+//                                          g's tile bbox; indexes the backward pass' gradient rows
+//   q1 = { a/2, b, c/2, hx }               conic with the 1/2 of sigma folded in
+//   q2 = { r, g, b, hy }
+// (hx, hy) are CONSERVATIVE half-extents, in pixels, of the region where this Gaussian can reach
+// alpha >= 1/255, i.e. of the ellipse sigma <= smax, smax = ln(255*opacity):
+//   hx = sqrt(2 smax c / (ac - b^2)), hy = sqrt(2 smax a / (ac - b^2))   (+ margin).
+// They let a warp skip whole records / pixel-row pairs that cannot contribute.  Culling never changes
+// results: the exact alpha < 1/255 test of the reference still decides every surviving pair.
 struct __align__(16) GsbRecord {
     float4 q0, q1, q2;
 };
 static_assert(sizeof(GsbRecord) == 48, "record must be 48 bytes");
 
-// Blend-kernel geometry: one WARP owns one 16x16 tile; lane l owns column (l & 15) and the 8 rows
-// 2*j + (l >> 4), j = 0..7.  No block-level synchronisation anywhere in the blend loops.
-constexpr int RK_WARPS = 4;            // tiles per CTA
+// Blend-kernel geometry: one WARP owns one 16x16 tile at a time (persistent warps pull tile ids from
+// a global counter); lane l owns column (l & 15) and the 8 rows 2*j + (l >> 4), j = 0..7 ("slot" j =
+// the two pixel rows 2j, 2j+1).  No block-level synchronisation anywhere in the blend loops.
+constexpr int RK_WARPS = 4;            // warps per CTA
 constexpr int RK_THREADS = RK_WARPS * 32;
 constexpr int RK_PIX = 8;              // pixels per lane
-constexpr int RK_CHUNK = 32;           // records per TMA bulk copy (1536 B)
+constexpr int RK_CHUNK = 32;           // records per TMA bulk copy (1536 B) == one record per lane
 constexpr int RK_STAGES = 4;           // ring depth per warp
 
-// per-intersection gradient row written by the backward blend kernel (48 B, indexed by k):
-//   { v_x, v_y, v_conic_a, v_conic_b, v_conic_c, v_r, v_g, v_b, v_opacity, 0, 0, 0 }
+constexpr float GSB_LN2 = 0.6931471805599453f;
+constexpr float GSB_LOG2E = 1.4426950408889634f;
+// smax = ln(255*opac) + 1e-3 = log2(opac)*ln2 + (ln 255 + 1e-3); the +1e-3 keeps the pre-test
+// conservative w.r.t. the rounding of sigma and of ex2.approx
+constexpr float GSB_SMAX_BIAS = 5.541263545158426f + 1e-3f;
+
+// per-intersection gradient row written by the backward blend kernel (48 B, indexed by k).  With
+// w = (unclamped alpha) * v_alpha and d = centre - pixel, summed over the tile's pixels:
+//   { S0 = sum w, Sx = sum w dx, Sy = sum w dy, Sxx = sum w dx^2, Sxy = sum w dx dy, Syy = sum w dy^2,
+//     R, G, B = sum alpha*T*v_out, 0, 0, 0 }
+// The (linear) map to v_xy / v_conic / v_opacity is applied once per Gaussian by the row-reduce kernel.
 constexpr int GSB_GRAD_ROW_FLOATS = 12;
+
+struct __align__(128) WarpRing {
+    GsbRecord rec[RK_STAGES][RK_CHUNK];
+    uint64_t full[RK_STAGES];
+};
+
+#ifdef __CUDACC__
+// Per-lane cull of record `lane` of a chunk against this warp's tile: returns the 8-bit mask of slots
+// (row pairs) whose rows intersect the record's y-extent, or 0 if the record cannot touch the tile.
+__device__ __forceinline__ unsigned record_slot_mask(const GsbRecord &r, float tile_x0, float tile_y0) {
+    const float gx = r.q0.x - tile_x0, gy = r.q0.y - tile_y0;   // centre in tile-local pixel coords
+    const float hx = r.q1.w, hy = r.q2.w;
+    // pixel centres of the tile are 0..15 in both axes
+    const bool hit_x = (gx + hx >= 0.f) && (gx - hx <= 15.f);
+    const float ylo = fmaxf(ceilf(gy - hy), 0.f), yhi = fminf(floorf(gy + hy), 15.f);
+    if (!hit_x || !(ylo <= yhi)) return 0u;
+    const int jlo = (int)ylo >> 1, jhi = (int)yhi >> 1;
+    return ((2u << jhi) - 1u) & ~((1u << jlo) - 1u);
+}
+#endif

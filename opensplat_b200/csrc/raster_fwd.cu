@@ -10,11 +10,17 @@
 // per-pixel global colour gathers):
 //  * a pack kernel turns the sorted id list into a contiguous 48-B record stream (raster_common.cuh),
 //    so a tile's list is one contiguous byte range;
-//  * one warp owns one tile and streams its range into a private 4-stage shared-memory ring with
-//    1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers -- no __syncthreads,
-//    no per-thread gather instructions in the blend loop;
-//  * each lane carries 8 pixels in registers (8 independent dependency chains), and every record
-//    is read once per warp with three broadcast 128-bit shared loads.
+//  * persistent warps pull tile ids from a global counter (no wave quantisation, no tail of idle SMs);
+//    one warp owns one tile and streams its range into a private 4-stage shared-memory ring with 1-D
+//    TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers -- no __syncthreads and no
+//    per-thread gather instructions in the blend loop;
+//  * each lane carries 8 pixels in registers; every surviving record is read once per warp with three
+//    broadcast 128-bit shared loads;
+//  * two levels of conservative culling before any per-pixel work: each lane tests ONE record of the
+//    32-record chunk against the tile (extent boxes stored in the record) and the warp then walks only
+//    the surviving records, visiting only the pixel-row pairs inside the record's y-extent; per pixel,
+//    sigma <= smax is tested before the exp.  ~25 % of (tile, Gaussian) records and ~2/3 of the row
+//    pairs of a typical 1080p scene never reach the exact alpha test.
 #include "raster_common.cuh"
 
 namespace {
@@ -29,36 +35,36 @@ pack_records_kernel(int m, const int *__restrict__ gaussian_ids_sorted,
     const int g = gaussian_ids_sorted[i];
     const int k = sorted_index ? sorted_index[i] : i;
     const float2 xy = __ldg(xys + g);
-    GsbRecord r;
+    const float a = __ldg(conics + 3 * g), b = __ldg(conics + 3 * g + 1), c = __ldg(conics + 3 * g + 2);
     const float opac = __ldg(opacities + g);
-    // alpha >= 1/255  <=>  sigma <= ln(255 * opac); +1e-3 keeps the pre-test conservative w.r.t. the
-    // rounding of sigma and of ex2.approx (the exact alpha test still runs inside the branch)
-    const float smax = fmaxf(0.f, __logf(255.f * fmaxf(opac, 1e-30f)) + 1e-3f);  // >= +0: compared as unsigned bits
-    r.q0 = make_float4(xy.x, xy.y, opac, __int_as_float(k));
-    r.q1 = make_float4(0.5f * __ldg(conics + 3 * g), __ldg(conics + 3 * g + 1), 0.5f * __ldg(conics + 3 * g + 2),
-                       smax);
-    r.q2 = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2),
-                       __int_as_float(g));
+    const float lo = (opac > 0.f) ? log2f(opac) : -INFINITY;
+    // extent of {sigma <= smax}: conservative (x1.001 + 0.01 px); no culling for degenerate conics
+    const float smax = fmaxf(0.f, fmaf(lo, GSB_LN2, GSB_SMAX_BIAS));
+    const float det = a * c - b * b;
+    float hx = INFINITY, hy = INFINITY;
+    if (det > 0.f && a > 0.f && c > 0.f) {
+        const float s2 = 2.f * smax / det;
+        hx = sqrtf(s2 * c) * 1.001f + 0.01f;
+        hy = sqrtf(s2 * a) * 1.001f + 0.01f;
+    }
+    GsbRecord r;
+    r.q0 = make_float4(xy.x, xy.y, lo, __int_as_float(k));
+    r.q1 = make_float4(0.5f * a, b, 0.5f * c, hx);
+    r.q2 = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), hy);
     float4 *dst = reinterpret_cast<float4 *>(records + i);
     stg_stream4(dst, r.q0);
     stg_stream4(dst + 1, r.q1);
     stg_stream4(dst + 2, r.q2);
 }
 
-struct __align__(128) WarpRing {
-    GsbRecord rec[RK_STAGES][RK_CHUNK];
-    uint64_t full[RK_STAGES];
-};
-
 __global__ void __launch_bounds__(RK_THREADS)
 rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                          const int2 *__restrict__ tile_bins, const GsbRecord *__restrict__ records,
                          const float *__restrict__ background, float *__restrict__ out_img,
-                         float *__restrict__ final_Ts, int *__restrict__ final_idx) {
+                         float *__restrict__ final_Ts, int *__restrict__ final_idx,
+                         unsigned *__restrict__ tile_counter) {
     __shared__ WarpRing rings[RK_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * RK_WARPS + warp;
-    if (tile >= num_tiles) return;
     WarpRing &ring = rings[warp];
     if (lane == 0) {
 #pragma unroll
@@ -66,105 +72,132 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         mbar_fence_init();
     }
     __syncwarp();
+    const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+    unsigned gchunk = 0;  // chunks this warp has pushed through its ring so far (stage / parity bookkeeping)
 
-    const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int X = tx * GSB_TILE + (lane & 15);
-    const int Y0 = ty * GSB_TILE + (lane >> 4);
-    const float px = (float)X;
-    const int2 range = tile_bins[tile];
-    const int L = range.y - range.x;
-    const int nchunks = (L + RK_CHUNK - 1) / RK_CHUNK;
+    while (true) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= num_tiles) break;
 
-    // T[j] > 0: transmittance of a live pixel.  A finished pixel keeps its final transmittance NEGATED
-    // (sign bit == "done"), so the hot loop needs no separate done test: T*(1-alpha) <= 1e-4 sends it
-    // to the (rare) terminate branch, which ignores pixels that are already negative.
-    float T[RK_PIX], cr[RK_PIX], cg[RK_PIX], cb[RK_PIX], py[RK_PIX];
-    int last[RK_PIX];
-    unsigned done = 0;  // bit j: pixel j finished (or outside the image)
+        const int tx = tile % tiles_x, ty = tile / tiles_x;
+        const int X = tx * GSB_TILE + (lane & 15);
+        const int Y0 = ty * GSB_TILE + (lane >> 4);
+        const float px = (float)X;
+        const float tile_x0 = (float)(tx * GSB_TILE), tile_y0 = (float)(ty * GSB_TILE);
+        const int2 range = tile_bins[tile];
+        const int L = range.y - range.x;
+        const int nchunks = (L + RK_CHUNK - 1) / RK_CHUNK;
+
+        // T[j] > 0: transmittance of a live pixel.  A finished pixel keeps its final transmittance
+        // NEGATED (sign bit == "done"): T*(1-alpha) <= 1e-4 then always routes it to the (rare)
+        // terminate branch, which ignores pixels that are already negative.
+        float T[RK_PIX], cr[RK_PIX], cg[RK_PIX], cb[RK_PIX], py[RK_PIX];
+        int last[RK_PIX];
+        unsigned done = 0;  // bit j: pixel j finished (or outside the image)
 #pragma unroll
-    for (int j = 0; j < RK_PIX; ++j) {
-        T[j] = 1.f; cr[j] = cg[j] = cb[j] = 0.f; last[j] = 0;
-        py[j] = (float)(Y0 + 2 * j);
-        if (X >= img_w || Y0 + 2 * j >= img_h) { done |= 1u << j; T[j] = -1.f; }
-    }
-
-    auto issue = [&](int c) {
-        if (lane == 0) {
-            const int s = c % RK_STAGES;
-            const int cnt = min(RK_CHUNK, L - c * RK_CHUNK);
-            const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(GsbRecord);
-            mbar_arrive_expect_tx(&ring.full[s], bytes);
-            tma_load_1d(&ring.rec[s][0], records + range.x + c * RK_CHUNK, bytes, &ring.full[s]);
+        for (int j = 0; j < RK_PIX; ++j) {
+            T[j] = 1.f; cr[j] = cg[j] = cb[j] = 0.f; last[j] = 0;
+            py[j] = (float)(Y0 + 2 * j);
+            if (X >= img_w || Y0 + 2 * j >= img_h) { done |= 1u << j; T[j] = -1.f; }
         }
-    };
 
-    const int pro = min(RK_STAGES, nchunks);
-    for (int c = 0; c < pro; ++c) issue(c);
-    int issued = pro;
+        const unsigned g0 = gchunk;  // ring position at tile start
+        auto stage_of = [&](int c) { return (g0 + (unsigned)c) % RK_STAGES; };
+        auto parity_of = [&](int c) { return ((g0 + (unsigned)c) / RK_STAGES) & 1u; };
+        auto issue = [&](int c) {
+            if (lane == 0) {
+                const int cnt = min(RK_CHUNK, L - c * RK_CHUNK);
+                const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(GsbRecord);
+                const unsigned s = stage_of(c);
+                mbar_arrive_expect_tx(&ring.full[s], bytes);
+                tma_load_1d(&ring.rec[s][0], records + range.x + c * RK_CHUNK, bytes, &ring.full[s]);
+            }
+        };
+        const int pro = min(RK_STAGES, nchunks);
+        for (int c = 0; c < pro; ++c) issue(c);
+        int issued = pro;
 
-    int c = 0;
-    for (; c < nchunks; ++c) {
-        const int s = c % RK_STAGES;
-        mbar_wait(&ring.full[s], (uint32_t)(c / RK_STAGES) & 1u);
-        const int cnt = min(RK_CHUNK, L - c * RK_CHUNK);
-        const int idx0 = range.x + c * RK_CHUNK;
-        for (int t = 0; t < cnt; ++t) {
-            const float4 q0 = ring.rec[s][t].q0;
-            const float4 q1 = ring.rec[s][t].q1;
-            const float4 q2 = ring.rec[s][t].q2;
-            const float dx = q0.x - px;
-            const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
-            const float bdx = q1.y * dx;
+        int c = 0;
+        for (; c < nchunks; ++c) {
+            const unsigned s = stage_of(c);
+            mbar_wait(&ring.full[s], parity_of(c));
+            const int cnt = min(RK_CHUNK, L - c * RK_CHUNK);
+            const int idx0 = range.x + c * RK_CHUNK;
+            // level-1 cull: lane l tests record l of the chunk against the tile
+            unsigned my_mask = 0;
+            if (lane < cnt) my_mask = record_slot_mask(ring.rec[s][lane], tile_x0, tile_y0);
+            unsigned live = __ballot_sync(0xffffffffu, my_mask != 0u);
+            while (live) {
+                const int t = __ffs(live) - 1;
+                live &= live - 1;
+                const unsigned rm = __shfl_sync(0xffffffffu, my_mask, t);  // slots inside the y-extent
+                const float4 q0 = ring.rec[s][t].q0;
+                const float4 q1 = ring.rec[s][t].q1;
+                const float4 q2 = ring.rec[s][t].q2;
+                const float smax = fmaxf(0.f, fmaf(q0.z, GSB_LN2, GSB_SMAX_BIAS));
+                const float dx = q0.x - px;
+                const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
+                const float bdx = q1.y * dx;
 #pragma unroll
-            for (int j = 0; j < RK_PIX; ++j) {
-                const float dy = q0.y - py[j];
-                // sigma = (a/2)dx^2 + (c/2)dy^2 + b dx dy   (forward.cu:340-342)
-                const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
-                if (__float_as_uint(sigma) <= __float_as_uint(q1.w)) {     // 0 <= sigma <= smax in ONE compare, no exp
-                    const float alpha = fminf(0.999f, q0.z * ex2_approx(sigma * -1.4426950408889634f));
-                    if (alpha >= (1.f / 255.f)) {
-                        const float next_T = T[j] * (1.f - alpha);
-                        if (next_T <= 1e-4f) {                          // terminate BEFORE blending
-                            if (T[j] > 0.f) { T[j] = -T[j]; done |= 1u << j; }
-                        } else {
-                            const float vis = alpha * T[j];
-                            cr[j] = fmaf(q2.x, vis, cr[j]);
-                            cg[j] = fmaf(q2.y, vis, cg[j]);
-                            cb[j] = fmaf(q2.z, vis, cb[j]);
-                            T[j] = next_T;
-                            last[j] = idx0 + t;
+                for (int j = 0; j < RK_PIX; ++j) {
+                    if (!((rm >> j) & 1u)) continue;                         // warp-uniform
+                    const float dy = q0.y - py[j];
+                    // sigma = (a/2)dx^2 + (c/2)dy^2 + b dx dy   (forward.cu:340-342)
+                    const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
+                    if (__float_as_uint(sigma) <= __float_as_uint(smax)) {    // 0 <= sigma <= smax, no exp
+                        // alpha = min(0.999, opac * exp(-sigma)) = min(0.999, 2^(log2 opac - sigma log2 e))
+                        const float alpha = fminf(0.999f, ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z)));
+                        if (alpha >= (1.f / 255.f)) {
+                            const float next_T = T[j] * (1.f - alpha);
+                            if (next_T <= 1e-4f) {                           // terminate BEFORE blending
+                                if (T[j] > 0.f) { T[j] = -T[j]; done |= 1u << j; }
+                            } else {
+                                const float vis = alpha * T[j];
+                                cr[j] = fmaf(q2.x, vis, cr[j]);
+                                cg[j] = fmaf(q2.y, vis, cg[j]);
+                                cb[j] = fmaf(q2.z, vis, cb[j]);
+                                T[j] = next_T;
+                                last[j] = idx0 + t;
+                            }
                         }
                     }
                 }
             }
+            if (__all_sync(0xffffffffu, done == 0xffu)) { ++c; break; }  // whole tile saturated
+            __syncwarp();
+            if (issued < nchunks) { issue(issued); ++issued; }
         }
-        if (__all_sync(0xffffffffu, done == 0xffu)) { ++c; break; }  // whole tile saturated
+        // drain bulk copies still in flight (early exit) so the ring can be reused by the next tile
+        for (; c < issued; ++c) mbar_wait(&ring.full[stage_of(c)], parity_of(c));
+        gchunk = g0 + (unsigned)issued;
         __syncwarp();
-        if (issued < nchunks) { issue(issued); ++issued; }
-    }
-    // drain bulk copies that are still in flight before the ring's shared memory is released
-    for (; c < issued; ++c) mbar_wait(&ring.full[c % RK_STAGES], (uint32_t)(c / RK_STAGES) & 1u);
 
-    const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
 #pragma unroll
-    for (int j = 0; j < RK_PIX; ++j) {
-        const int Y = Y0 + 2 * j;
-        if (X < img_w && Y < img_h) {
-            const size_t p = (size_t)Y * img_w + X;
-            const float Tf = fabsf(T[j]);
-            final_Ts[p] = Tf;
-            final_idx[p] = last[j];
-            out_img[3 * p] = cr[j] + Tf * bg0;
-            out_img[3 * p + 1] = cg[j] + Tf * bg1;
-            out_img[3 * p + 2] = cb[j] + Tf * bg2;
+        for (int j = 0; j < RK_PIX; ++j) {
+            const int Y = Y0 + 2 * j;
+            if (X < img_w && Y < img_h) {
+                const size_t p = (size_t)Y * img_w + X;
+                const float Tf = fabsf(T[j]);
+                final_Ts[p] = Tf;
+                final_idx[p] = last[j];
+                out_img[3 * p] = cr[j] + Tf * bg0;
+                out_img[3 * p + 1] = cg[j] + Tf * bg1;
+                out_img[3 * p + 2] = cb[j] + Tf * bg2;
+            }
         }
     }
 }
 
 }  // namespace
 
+int gsb_sm_count();
+int gsb_blend_grid(const void *kernel, int num_tiles);
+
 extern "C" size_t gsb_raster_records_bytes(int m) {
-    return gsb_align_up((size_t)(m > 0 ? m : 0) * sizeof(GsbRecord) + 256, 256);
+    // + 256 B of scratch at the end: the persistent blend kernels' tile counters
+    return gsb_align_up((size_t)(m > 0 ? m : 0) * sizeof(GsbRecord), 256) + 256;
 }
 
 extern "C" int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tiles_y, int m,
@@ -175,19 +208,47 @@ extern "C" int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tile
                                      float *final_Ts, int32_t *final_idx, gsb_stream_t stream) {
     GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0);
     GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
-    GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx);
+    GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx && records);
+    GSB_CHECK_ARG(((uintptr_t)records % 16) == 0);
     cudaStream_t s = (cudaStream_t)stream;
     if (m > 0) {
-        GSB_CHECK_ARG(gaussian_ids_sorted && xys && conics && colors && opacities && records);
-        GSB_CHECK_ARG(((uintptr_t)records % 16) == 0 && ((uintptr_t)xys % 8) == 0);
+        GSB_CHECK_ARG(gaussian_ids_sorted && xys && conics && colors && opacities);
+        GSB_CHECK_ARG(((uintptr_t)xys % 8) == 0);
         pack_records_kernel<<<gsb_div_up(m, 256), 256, 0, s>>>(
             m, gaussian_ids_sorted, sorted_index, reinterpret_cast<const float2 *>(xys), conics, colors,
             opacities, reinterpret_cast<GsbRecord *>(records));
     }
+    unsigned *counters = reinterpret_cast<unsigned *>(
+        reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
+    GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
     const int num_tiles = tiles_x * tiles_y;
-    rasterize_forward_kernel<<<gsb_div_up(num_tiles, RK_WARPS), RK_THREADS, 0, s>>>(
+    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel, num_tiles);
+    rasterize_forward_kernel<<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx);
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters);
     GSB_LAUNCH_CHECK();
     return 0;
+}
+
+// ---- shared launch helpers (also used by raster_bwd.cu) --------------------------------------
+int gsb_sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// persistent grid: SMs x resident CTAs per SM (never more CTAs than there are tile groups)
+int gsb_blend_grid(const void *kernel, int num_tiles) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RK_THREADS, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const int full = gsb_sm_count() * per_sm;
+    const int need = gsb_div_up(num_tiles, RK_WARPS);
+    return need < full ? need : full;
 }

@@ -200,8 +200,8 @@ def rasterize_forward(tile_bounds_, img_size, gaussian_ids_sorted, sorted_index,
     return out, fT, fI, records
 
 
-def rasterize_backward(img_height, img_width, n, m, tile_bins, records, cum_tiles_hit, background, final_Ts,
-                       final_idx, v_output, v_output_alpha=None):
+def rasterize_backward(img_height, img_width, n, m, tile_bins, conics, opacities, records, cum_tiles_hit,
+                       background, final_Ts, final_idx, v_output, v_output_alpha=None):
     L = capi.lib()
     tb = tile_bounds(img_width, img_height)
     rows = _ws.get(final_Ts.device, "grad_rows", L.gsb_raster_grad_rows_bytes(m) + 16)
@@ -212,8 +212,9 @@ def rasterize_backward(img_height, img_width, n, m, tile_bins, records, cum_tile
     v_opacity = _empty((n, 1), torch.float32, final_Ts)
     v_output = capi.f32(v_output)
     capi.check(L.gsb_rasterize_backward(
-        img_height, img_width, tb[0], tb[1], n, m, capi.ptr(tile_bins), capi.ptr(records),
-        capi.ptr(cum_tiles_hit), capi.ptr(capi.f32(background)), capi.ptr(final_Ts), capi.ptr(final_idx),
+        img_height, img_width, tb[0], tb[1], n, m, capi.ptr(tile_bins), capi.ptr(capi.f32(conics)),
+        capi.ptr(capi.f32(opacities)), capi.ptr(records), capi.ptr(cum_tiles_hit),
+        capi.ptr(capi.f32(background)), capi.ptr(final_Ts), capi.ptr(final_idx),
         capi.ptr(v_output), capi.ptr(v_output_alpha) if v_output_alpha is not None else None,
         rows.data_ptr() + off, capi.ptr(v_xy), capi.ptr(v_conic), capi.ptr(v_colors), capi.ptr(v_opacity),
         capi.stream()))
@@ -263,14 +264,15 @@ class RasterizeGaussians(torch.autograd.Function):
         out, fT, fI, records = rasterize_forward(tb, (imgWidth, imgHeight, 1), gs, idx, bins, xys, conics,
                                                  colors, opacity, background)
         ctx.meta = (int(imgHeight), int(imgWidth), numPoints, numIntersects)
-        ctx.save_for_backward(bins, records, cum, background, fT, fI)
+        ctx.save_for_backward(bins, conics, opacity, records, cum, background, fT, fI)
         return out
 
     @staticmethod
     def backward(ctx, v_outImg):
         H, W, n, m = ctx.meta
-        bins, records, cum, background, fT, fI = ctx.saved_tensors
-        v_xy, v_conic, v_colors, v_opacity = rasterize_backward(H, W, n, m, bins, records, cum, background, fT, fI,
+        bins, conics, opacity, records, cum, background, fT, fI = ctx.saved_tensors
+        v_xy, v_conic, v_colors, v_opacity = rasterize_backward(H, W, n, m, bins, conics, opacity, records, cum,
+                                                                background, fT, fI,
                                                                 v_outImg.contiguous(), None)
         # 10 slots; grads for xys(0), conics(3), colors(5), opacity(6) (rasterize_gaussians.cpp:129-139)
         return v_xy, None, None, v_conic, None, v_colors, v_opacity, None, None, None

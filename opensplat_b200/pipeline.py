@@ -182,8 +182,9 @@ class SplatPipeline:
         self.loss.zero_()
         capi.check(L.gsb_mse_loss_grad(cnt, P(self.out_img), P(self.target), P(self.v_img), P(self.loss), 1.0 / cnt, s))
         self._stage("raster_bwd")
-        capi.check(L.gsb_rasterize_backward(H, W, self.tb[0], self.tb[1], n, m, P(self.tile_bins), P(self.records),
-                                            P(self.cum), P(self.background), P(self.final_Ts), P(self.final_idx),
+        capi.check(L.gsb_rasterize_backward(H, W, self.tb[0], self.tb[1], n, m, P(self.tile_bins), P(self.conics),
+                                            P(p["opacities"]), P(self.records), P(self.cum), P(self.background),
+                                            P(self.final_Ts), P(self.final_idx),
                                             P(self.v_img), None, P(self.grad_rows), P(self.v_xy), P(self.v_conic),
                                             P(self.v_rgbs), P(g["opacities"]), s))
         # glue: gradient of clamp_min(colors + 0.5, 0)

@@ -165,14 +165,14 @@ def test_rasterize_forward_backward_vs_oracle(n, W, H, scale, opac, bg):
     # backward on the oracle's own final_Ts/final_idx (identical inputs to both sides)
     wgt = rng.uniform(-1, 1, (H, W, 3)).astype(np.float32)
     fTo, fIo = cu(o["final_Ts"]), cu(o["final_idx"])
-    v = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["rec"], st["cum"], st["bg"], fTo, fIo, cu(wgt))
+    v = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["conics"], cu(sc["opacities"]), st["rec"], st["cum"], st["bg"], fTo, fIo, cu(wgt))
     ob = orc.rasterize_backward(H, W, npy(st["gs"]), npy(st["bins"]), npy(st["xys"]), npy(st["conics"]), colors,
                                 sc["opacities"], bg, o["final_Ts"], o["final_idx"], wgt, exp_mode=1)
     tol = 2e-4 if opac[1] < 0.9 else 2e-3   # fp32 re-association; 1/(1-alpha) amplifies when alpha -> 0.99
     for a, b in zip(v, (ob["v_xy"], ob["v_conic"], ob["v_colors"], ob["v_opacity"])):
         assert rel_l2(npy(a), b) <= tol
     # deterministic: bit-identical on a second run (no atomics)
-    v2 = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["rec"], st["cum"], st["bg"], fTo, fIo, cu(wgt))
+    v2 = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["conics"], cu(sc["opacities"]), st["rec"], st["cum"], st["bg"], fTo, fIo, cu(wgt))
     for a, b in zip(v, v2):
         assert torch.equal(a, b)
 
@@ -185,7 +185,7 @@ def test_rasterize_v_output_alpha_term():
     (out, fT, fI), o, st = _raster_both(sc, colors, [0.2, 0.3, 0.4])
     wgt = rng.uniform(-1, 1, (H, W, 3)).astype(np.float32)
     wa = rng.uniform(-1, 1, (H, W)).astype(np.float32)
-    v = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["rec"], st["cum"], st["bg"], cu(o["final_Ts"]),
+    v = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["conics"], cu(sc["opacities"]), st["rec"], st["cum"], st["bg"], cu(o["final_Ts"]),
                                cu(o["final_idx"]), cu(wgt), cu(wa))
     ob = orc.rasterize_backward(H, W, npy(st["gs"]), npy(st["bins"]), npy(st["xys"]), npy(st["conics"]), colors,
                                 sc["opacities"], [0.2, 0.3, 0.4], o["final_Ts"], o["final_idx"], wgt, wa, exp_mode=1)
@@ -390,8 +390,8 @@ def test_full_size_properties_and_oracle(n, W, H, scale):
     assert ok, stats
     rng = np.random.default_rng(0)
     wgt = cu(rng.uniform(-1, 1, (H, W, 3)).astype(np.float32))
-    v = ops.rasterize_backward(H, W, n, m, bins, rec, cum, bg, fT, fI, wgt)
-    v2 = ops.rasterize_backward(H, W, n, m, bins, rec, cum, bg, fT, fI, wgt * 2)
+    v = ops.rasterize_backward(H, W, n, m, bins, conics, opac, rec, cum, bg, fT, fI, wgt)
+    v2 = ops.rasterize_backward(H, W, n, m, bins, conics, opac, rec, cum, bg, fT, fI, wgt * 2)
     for a, b in zip(v, v2):
         assert torch.equal(a * 2, b)                                    # backward is linear in v_output
     orb = orc.rasterize_backward(H, W, npy(gs), binsn, npy(xys), npy(conics), npy(rgbs), sc["opacities"], [0, 0, 0],
