@@ -215,6 +215,8 @@ def run_ours(args):
         sampler.start()
     ms_total = timed(step_fwd_bwd, args.steps)
     stage_ms = pipe.resolve_stage_times()
+    m_timed = pipe.m
+    alg, passes = pipe.algorithmic_bytes()
     ms_step = ms_total / args.steps
     value = world * W * H / (ms_step * 1e-3) / 1e6
 
@@ -232,16 +234,26 @@ def run_ours(args):
     bg = torch.zeros(3, device=dev)
     loss_host = torch.zeros(1).pin_memory()
 
+    from opensplat_b200 import cpp_ops
+    use_cpp = cpp_ops.available()
+    cops = cpp_ops.ops() if use_cpp else None
+
     def step_e2e():
         tgt = target_host.to(dev, non_blocking=True)             # H2D: this step's target image
         vm = view_host.to(dev, non_blocking=True)                # H2D: this step's camera
         pm = proj_host.to(dev, non_blocking=True)
         for t in P.values():
             t.grad = None
-        rgbs = torch.clamp_min(ops.SphericalHarmonics.apply(3, pipe.viewdirs, P["coeffs"]) + 0.5, 0.0)
-        xys, depths, radii, conics, nth, _ = ops.ProjectGaussians.apply(
-            P["means"], P["scales"], 1.0, P["quats"], vm, pm, fx, fy, cx, cy, H, W, pipe.tb)
-        img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, rgbs, P["opacities"], H, W, bg)
+        if use_cpp:   # the libtorch autograd operators a C++ caller of the reference API uses
+            rgbs = torch.clamp_min(cops.spherical_harmonics(3, pipe.viewdirs, P["coeffs"]) + 0.5, 0.0)
+            xys, depths, radii, conics, nth, _ = cops.project_gaussians(
+                P["means"], P["scales"], 1.0, P["quats"], vm, pm, fx, fy, cx, cy, H, W, 0.01)
+            img = cops.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, P["opacities"], H, W, bg)
+        else:
+            rgbs = torch.clamp_min(ops.SphericalHarmonics.apply(3, pipe.viewdirs, P["coeffs"]) + 0.5, 0.0)
+            xys, depths, radii, conics, nth, _ = ops.ProjectGaussians.apply(
+                P["means"], P["scales"], 1.0, P["quats"], vm, pm, fx, fy, cx, cy, H, W, pipe.tb)
+            img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, rgbs, P["opacities"], H, W, bg)
         loss = torch.nn.functional.mse_loss(img, tgt)
         loss.backward()
         if world > 1:
@@ -257,7 +269,6 @@ def run_ours(args):
     e2e_value = world * W * H / (ms_e2e * 1e-3) / 1e6
 
     # ---- roofline of the dominant stage ----
-    alg, passes = pipe.algorithmic_bytes()
     peak, peak_src = peaks()
     dom = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else "raster_bwd"
     dom_key = dom if dom in alg else "raster_bwd"
@@ -291,14 +302,16 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "gaussians": n, "width": W, "height": H, "sh_degree": 3,
-                   "intersections_M": pipe.m, "views_per_gpu": 1, "parallelism": f"dp{world}-views",
+                   "intersections_M": m_timed, "views_per_gpu": 1, "parallelism": f"dp{world}-views",
                    "step": "sh+project+scan/emit/sort/bins+blend fwd, mse, blend+project+sh bwd"
                            + (", nccl allreduce(flat grads)" if world > 1 else ""),
                    "l2_policy": "inputs larger than L2 (>300 MB of parameters/records per step vs 126 MB L2)"},
         "train_iters_per_s": 1e3 / ms_train, "train_ms_per_iter": ms_train,
         "e2e": {"value": e2e_value, "unit": "Mpixel/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(target_host.numel() * 4 + 128), "d2h_bytes_per_step": 4 + 4,
-                "api": "opensplat_b200.ops autograd operators (SphericalHarmonics/ProjectGaussians/RasterizeGaussians)"},
+                "api": ("C++ libtorch autograd operators ProjectGaussians/RasterizeGaussians/SphericalHarmonics "
+                        "(libopensplat_b200_ops.so via torch.ops)") if use_cpp else
+                       "opensplat_b200.ops python autograd operators"},
         "gpu_launches": launches_per_step(passes) * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_key, "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -1,0 +1,43 @@
+// register.cpp -- exposes the C++ autograd operators to Python as torch.ops.opensplat_b200.* so that the
+// parity tests and bench.py's e2e arm can drive the SAME libtorch operator classes a C++ caller
+// (model.cpp / simple_trainer.cpp) uses.
+#include <torch/library.h>
+#include "project_gaussians.hpp"
+#include "rasterize_gaussians.hpp"
+#include "spherical_harmonics.hpp"
+
+static std::vector<torch::Tensor> op_project(torch::Tensor means, torch::Tensor scales, double globScale,
+                                             torch::Tensor quats, torch::Tensor viewMat, torch::Tensor projMat,
+                                             double fx, double fy, double cx, double cy, int64_t imgHeight,
+                                             int64_t imgWidth, double clipThresh) {
+    TileBounds tb = std::make_tuple((int)(imgWidth + BLOCK_X - 1) / BLOCK_X, (int)(imgHeight + BLOCK_Y - 1) / BLOCK_Y, 1);
+    return ProjectGaussians::apply(means, scales, (float)globScale, quats, viewMat, projMat, (float)fx, (float)fy,
+                                   (float)cx, (float)cy, (int)imgHeight, (int)imgWidth, tb, (float)clipThresh);
+}
+
+static torch::Tensor op_rasterize(torch::Tensor xys, torch::Tensor depths, torch::Tensor radii,
+                                  torch::Tensor conics, torch::Tensor numTilesHit, torch::Tensor colors,
+                                  torch::Tensor opacity, int64_t imgHeight, int64_t imgWidth,
+                                  torch::Tensor background) {
+    return RasterizeGaussians::apply(xys, depths, radii, conics, numTilesHit, colors, opacity, (int)imgHeight,
+                                     (int)imgWidth, background);
+}
+
+static torch::Tensor op_sh(int64_t degreesToUse, torch::Tensor viewDirs, torch::Tensor coeffs) {
+    return SphericalHarmonics::apply((int)degreesToUse, viewDirs, coeffs);
+}
+
+static std::vector<torch::Tensor> op_bin_and_sort(int64_t numPoints, int64_t numIntersects, torch::Tensor xys,
+                                                  torch::Tensor depths, torch::Tensor radii,
+                                                  torch::Tensor cumTilesHit, int64_t tilesX, int64_t tilesY) {
+    auto t = binAndSortGaussians((int)numPoints, (int)numIntersects, xys, depths, radii, cumTilesHit,
+                                 std::make_tuple((int)tilesX, (int)tilesY, 1));
+    return {std::get<0>(t), std::get<1>(t), std::get<2>(t), std::get<3>(t), std::get<4>(t)};
+}
+
+TORCH_LIBRARY(opensplat_b200, m) {
+    m.def("project_gaussians", &op_project);
+    m.def("rasterize_gaussians", &op_rasterize);
+    m.def("spherical_harmonics", &op_sh);
+    m.def("bin_and_sort_gaussians", &op_bin_and_sort);
+}

@@ -1,0 +1,124 @@
+"""GPU: the C++/libtorch operator layer (the actual drop-in: same class names / signatures as the
+reference's project_gaussians.hpp, rasterize_gaussians.hpp, spherical_harmonics.hpp) and the reference's
+UNCHANGED simple_trainer.cpp compiled against it."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from opensplat_b200 import cpp_ops, ops
+from util import load_golden, rel_l2, image_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("name,gtol", [("chain_tight_100x72", 2e-3), ("chain_bg_quat_128x96", 2e-3)])
+def test_cpp_operator_chain_vs_reference_golden(name, gtol):
+    g = load_golden(name)
+    o = cpp_ops.ops()
+    fx, fy, cx, cy = [float(v) for v in g["intrins"]]
+    H, W = [int(v) for v in g["hw"]]
+    means, scales, quats = (cu(g[k]).requires_grad_() for k in ("means", "scales", "quats"))
+    colors, opac = cu(g["colors"]).requires_grad_(), cu(g["opacities"]).requires_grad_()
+    xys, depths, radii, conics, nth, cov3d = o.project_gaussians(means, scales, 1.0, quats, cu(g["viewmat"]),
+                                                                 cu(g["projmat"]), fx, fy, cx, cy, H, W, 0.01)
+    xys.retain_grad()
+    img = o.rasterize_gaussians(xys, depths, radii, conics, nth, colors, opac, H, W, cu(g["background"]))
+    ok, stats = image_close(img.detach().cpu().numpy(), g["ref_img"], tol=5e-5)
+    assert ok, stats
+    (img * cu(g["wgt"])).sum().backward()
+    for got, ref in [(xys.grad, "ref_v_xy"), (colors.grad, "ref_v_colors"), (opac.grad, "ref_v_opacity"),
+                     (means.grad, "ref_v_means"), (scales.grad, "ref_v_scales"), (quats.grad, "ref_v_quats")]:
+        assert rel_l2(got.cpu().numpy(), g[ref]) <= gtol
+    # the python mirror drives the same C ABI -> bit-identical
+    m2, s2, q2 = (cu(g[k]).requires_grad_() for k in ("means", "scales", "quats"))
+    c2, o2 = cu(g["colors"]).requires_grad_(), cu(g["opacities"]).requires_grad_()
+    p = ops.ProjectGaussians.apply(m2, s2, 1.0, q2, cu(g["viewmat"]), cu(g["projmat"]), fx, fy, cx, cy, H, W,
+                                   ops.tile_bounds(W, H))
+    img2 = ops.RasterizeGaussians.apply(p[0], p[1], p[2], p[3], p[4], c2, o2, H, W, cu(g["background"]))
+    (img2 * cu(g["wgt"])).sum().backward()
+    assert torch.equal(img, img2) and torch.equal(means.grad, m2.grad) and torch.equal(quats.grad, q2.grad)
+
+
+def test_cpp_sh_and_bin_and_sort():
+    o = cpp_ops.ops()
+    g = load_golden("sh_deg3")
+    co = cu(g["coeffs"]).requires_grad_()
+    col = o.spherical_harmonics(3, cu(g["viewdirs"]), co)
+    (col * cu(g["wgt"])).sum().backward()
+    assert np.abs(col.detach().cpu().numpy() - g["ref_colors_d3"]).max() <= 2e-5
+    assert np.abs(co.grad.cpu().numpy() - g["ref_v_coeffs_d3"]).max() <= 2e-6
+    gg = load_golden("chain_tight_100x72")
+    fx, fy, cx, cy = [float(v) for v in gg["intrins"]]
+    H, W = [int(v) for v in gg["hw"]]
+    xys, depths, radii, conics, nth, _ = o.project_gaussians(cu(gg["means"]), cu(gg["scales"]), 1.0, cu(gg["quats"]),
+                                                             cu(gg["viewmat"]), cu(gg["projmat"]), fx, fy, cx, cy, H, W,
+                                                             0.01)
+    cum = torch.cumsum(nth, 0, dtype=torch.int32)
+    tb = ops.tile_bounds(W, H)
+    isect, gids, ks, gs, bins = o.bin_and_sort_gaussians(xys.shape[0], int(cum[-1]), xys, depths, radii, cum, tb[0], tb[1])
+    ref = torch.sort(isect, stable=True)
+    assert torch.equal(ks, ref.values) and torch.equal(gs, gids[ref.indices])
+
+
+def _python_simple_trainer(width, height, n, iters, lr=0.01):
+    """simple_trainer.cpp:84-203 restated with the python mirror operators (same seeds, same math)."""
+    torch.manual_seed(0)
+    gt = torch.ones(height, width, 3)
+    gt[: height // 2, : width // 2, :] = torch.tensor([1.0, 0.0, 0.0])
+    gt[height // 2:, width // 2:, :] = torch.tensor([0.0, 0.0, 1.0])
+    gt = gt.to(DEV)
+    focal = 0.5 * width / np.tan(0.5 * np.pi / 2.0)
+    means = 2.0 * (torch.rand(n, 3) - 0.5)
+    scales = torch.rand(n, 3)
+    rgbs = torch.rand(n, 3)
+    u, v, w = torch.rand(n, 1), torch.rand(n, 1), torch.rand(n, 1)
+    means, scales, rgbs, u, v, w = (t.to(DEV) for t in (means, scales, rgbs, u, v, w))
+    quats = torch.cat([torch.sqrt(1 - u) * torch.sin(2 * np.pi * v), torch.sqrt(1 - u) * torch.cos(2 * np.pi * v),
+                       torch.sqrt(u) * torch.sin(2 * np.pi * w), torch.sqrt(u) * torch.cos(2 * np.pi * w)], -1)
+    opac = torch.ones(n, 1, device=DEV)
+    view = torch.eye(4, device=DEV)
+    view[2, 3] = 8.0
+    bg = torch.zeros(3, device=DEV)
+    for t in (means, scales, quats, rgbs, opac):
+        t.requires_grad_()
+    opt = torch.optim.Adam([rgbs, means, scales, opac, quats], lr, foreach=False)
+    tb = ops.tile_bounds(width, height)
+    losses = []
+    for _ in range(iters):
+        p = ops.ProjectGaussians.apply(means, scales, 1, quats, view, view, focal, focal, width // 2, height // 2,
+                                       height, width, tb)
+        img = ops.RasterizeGaussians.apply(p[0], p[1], p[2], p[3], p[4], torch.sigmoid(rgbs), torch.sigmoid(opac),
+                                           height, width, bg)
+        loss = torch.nn.functional.mse_loss(img, gt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    return losses
+
+
+def test_reference_simple_trainer_unchanged_runs_on_b200_backend():
+    exe = os.path.join(ROOT, "opensplat_b200", "lib", "simple_trainer_b200")
+    if not os.path.exists(exe):
+        pytest.skip("simple_trainer_b200 not built (needs /root/reference at build time)")
+    iters, n, W, H = 30, 2000, 256, 256
+    r = subprocess.run([exe, "--width", str(W), "--height", str(H), "--points", str(n), "--iters", str(iters)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Using CUDA" in r.stdout
+    losses = [float(x) for x in re.findall(r"Loss: ([0-9.eE+-]+)", r.stdout)]
+    assert len(losses) == iters
+    assert losses[-1] < 0.8 * losses[0]                      # it trains
+    py = _python_simple_trainer(W, H, n, iters)
+    assert abs(py[0] - losses[0]) <= 1e-5 * max(1.0, abs(py[0]))   # same forward on the same seeded scene
+    assert np.abs(np.array(py) - np.array(losses)).max() <= 2e-3 * max(py)  # same trajectory
