@@ -109,6 +109,31 @@ int gsb_gather_bin_edges(int m, int num_tiles, const int64_t *isect_ids_sorted,
                          const int32_t *sorted_index, const int32_t *gaussian_ids,
                          int32_t *gaussian_ids_sorted, int32_t *tile_bins, gsb_stream_t stream);
 
+/* ---- Tile binning, fast path: two-level bucket sort fused with record packing ------------------
+ * Produces the SAME tile_bins and the SAME per-tile order (tile, then depth bits, ties by ascending
+ * unsorted slot) as gsb_map_gaussian_to_intersects + gsb_sort_intersects + gsb_gather_bin_edges +
+ * the record packing of gsb_rasterize_forward, without a global sort (what RasterizeGaussians::forward
+ * needs between rasterize_gaussians.cpp:62 and :79).
+ * gsb_bucket_tile_ranges (before the M read-back): tile_bins [tiles,2], tile_cursor [tiles] (scratch that
+ *   phase 2 consumes) and stats[2] = {M, longest tile list} (device int32; read both back in the operator's
+ *   single D2H copy).
+ * gsb_bucket_sort_pack (after it): fills `records` (gsb_raster_records_bytes(m)); optional outputs
+ *   sorted_index [m] / gaussian_ids_sorted [m] (NULL to skip).  Returns GSB_ERR_UNSUPPORTED if
+ *   max_tile_len > gsb_bucket_max_tile_len() -- take the generic path then.
+ * gsb_rasterize_forward_packed: the blend kernel alone on an already packed record stream. */
+int gsb_bucket_max_tile_len(void);
+size_t gsb_bucket_workspace_bytes(int m);
+int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
+                           int32_t *tile_bins, int32_t *tile_cursor, int32_t *stats, gsb_stream_t stream);
+int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float *xys, const float *depths,
+                         const int32_t *radii, const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
+                         const int32_t *tile_bins, int32_t *tile_cursor, const float *conics, const float *colors,
+                         const float *opacities, void *workspace, size_t workspace_bytes, void *records,
+                         int32_t *sorted_index, int32_t *gaussian_ids_sorted, gsb_stream_t stream);
+int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, int tiles_y, int m,
+                                 const int32_t *tile_bins, const float *background, void *records,
+                                 float *out_img, float *final_Ts, int32_t *final_idx, gsb_stream_t stream);
+
 /* ---- Rasterization ---------------------------------------------------------------------------
  * gsb_rasterize_forward replaces rasterize_forward_tensor (bindings.h:110-125, bindings.cu:338-410,
  *   kernel forward.cu:256-378).  Inputs as the reference (gaussian_ids_sorted [m], tile_bins

@@ -20,6 +20,7 @@ SOURCES = {
     "sh.cu": [],
     "project.cu": ["--fmad=false"],
     "binning.cu": [],
+    "bucket.cu": [],
     "raster_fwd.cu": [],
     "raster_bwd.cu": [],
     "fused.cu": [],

@@ -35,6 +35,12 @@ _SIGS = {
                                    _vp, _vp, _vp]),
     "gsb_rasterize_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_bucket_max_tile_len": (_i, []),
+    "gsb_bucket_workspace_bytes": (_sz, [_i]),
+    "gsb_bucket_tile_ranges": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "gsb_bucket_sort_pack": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
+                                  _vp, _vp]),
+    "gsb_rasterize_forward_packed": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_adam_step": (_i, [C.c_longlong, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp]),
     "gsb_mse_loss_grad": (_i, [C.c_longlong, _vp, _vp, _vp, _vp, _f, _vp]),
 }

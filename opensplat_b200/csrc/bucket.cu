@@ -1,0 +1,244 @@
+// bucket.cu -- two-level tile binning fused with record packing (fast path of B2+B3+B4 + pack).
+//
+// The reference sorts all M intersections globally on the 64-bit key (tile_id << 32 | depth bits)
+// (rasterize_gaussians.cpp:25-32) and then finds tile boundaries (forward.cu:148-169).  The same
+// ORDER -- by tile, then depth bits, ties by ascending unsorted slot k (what a stable sort of the
+// Gaussian-major emission gives) -- is produced here without a global sort:
+//   K1 tile_count   : per Gaussian, one atomic per covered tile  -> tile sizes
+//   K2 tile_scan    : exclusive scan over the T tiles            -> tile_bins (first, last+1) directly, max length
+//   K3 bucket_emit  : per Gaussian, write (depth bits << 32 | k) into its tiles' segments (atomic cursor;
+//                     arrival order is arbitrary, the composite key makes the final order unique)
+//   K4 tile_sort_pack: one CTA per tile sorts its segment in shared memory (bitonic, 64-bit composites),
+//                     then gathers the Gaussian attributes and writes the 48-B record stream directly.
+// Per-intersection HBM traffic drops from (8 + 6*24 + 8 + 12 + 84) B of the emit / 6-pass radix / bins /
+// pack sequence to 8 B written + 8 B read of composites (L2-resident) + 36 B gathered + 48 B written.
+// Integer work, L2/HBM-bound; results (tile_bins, per-tile order) are bit-identical to the generic
+// path (tests/test_gpu_parity.py::test_bucket_binning_matches_generic_sort).
+#include "raster_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void tile_bbox_of(float2 c, int r, int tiles_x, int tiles_y, int &x0, int &x1, int &y0,
+                                             int &y1) {
+    // get_tile_bbox (helpers.cuh:17-49) -- same arithmetic as project.cu / binning.cu
+    const float tcx = c.x / 16.f, tcy = c.y / 16.f, tr = (float)r / 16.f;
+    x0 = min(max(0, (int)(tcx - tr)), tiles_x);
+    x1 = min(max(0, (int)(tcx + tr + 1.f)), tiles_x);
+    y0 = min(max(0, (int)(tcy - tr)), tiles_y);
+    y1 = min(max(0, (int)(tcy + tr + 1.f)), tiles_y);
+}
+
+__global__ void __launch_bounds__(256)
+tile_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii, int tiles_x,
+                  int tiles_y, int *__restrict__ tile_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = radii[i];
+    if (r <= 0) return;
+    int x0, x1, y0, y1;
+    tile_bbox_of(xys[i], r, tiles_x, tiles_y, x0, x1, y0, y1);
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) atomicAdd(&tile_count[ty * tiles_x + tx], 1);
+}
+
+// single CTA: exclusive scan of tile_count -> tile_bins; zeroes the cursors; max tile length
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int T, int *__restrict__ tile_count_then_cursor, int2 *__restrict__ tile_bins,
+                 int *__restrict__ stats /* [0] = total, [1] = max length */) {
+    __shared__ int sm[33];
+    __shared__ int s_max;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    int carry = 0, my_max = 0;
+    for (int base = 0; base < T; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < T) ? tile_count_then_cursor[i] : 0;
+        my_max = max(my_max, v);
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) sm[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int x = sm[lane];
+            int xi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, xi, o);
+                if (lane >= o) xi += t;
+            }
+            sm[lane] = xi - x;
+            if (lane == 31) sm[32] = xi;
+        }
+        __syncthreads();
+        const int excl = carry + sm[w] + inc - v;
+        if (i < T) {
+            // empty tiles keep (0,0) like the reference's zero-initialised tile_bins
+            tile_bins[i] = (v > 0) ? make_int2(excl, excl + v) : make_int2(0, 0);
+            tile_count_then_cursor[i] = excl;   // becomes the write cursor of K3
+        }
+        carry += sm[32];
+        __syncthreads();
+    }
+    atomicMax(&s_max, my_max);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        stats[0] = carry;
+        stats[1] = s_max;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bucket_emit_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__ depths,
+                   const int *__restrict__ radii, const int *__restrict__ cum_tiles_hit, int tiles_x,
+                   int tiles_y, int *__restrict__ cursor, unsigned long long *__restrict__ comp,
+                   int *__restrict__ gaussian_ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = radii[i];
+    if (r <= 0) return;
+    int x0, x1, y0, y1;
+    tile_bbox_of(xys[i], r, tiles_x, tiles_y, x0, x1, y0, y1);
+    int k = (i == 0) ? 0 : cum_tiles_hit[i - 1];
+    const unsigned long long hi = ((unsigned long long)(unsigned)__float_as_int(depths[i])) << 32;
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) {
+            const int pos = atomicAdd(&cursor[ty * tiles_x + tx], 1);
+            comp[pos] = hi | (unsigned)k;
+            gaussian_ids[k] = i;
+            ++k;
+        }
+}
+
+__global__ void __launch_bounds__(256)
+tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
+                      const int *__restrict__ gaussian_ids, const float2 *__restrict__ xys,
+                      const float *__restrict__ conics, const float *__restrict__ colors,
+                      const float *__restrict__ opacities, GsbRecord *__restrict__ records,
+                      int *__restrict__ sorted_index, int *__restrict__ gaussian_ids_sorted) {
+    extern __shared__ unsigned long long skey[];
+    const int tile = blockIdx.x;
+    const int2 range = tile_bins[tile];
+    const int L = range.y - range.x;
+    if (L <= 0) return;
+    int n2 = 1;
+    while (n2 < L) n2 <<= 1;
+    if (n2 > cap) return;  // host guarantees max length <= cap (otherwise it takes the generic path)
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) skey[i] = (i < L) ? comp[range.x + i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                // t-th compare-exchange of this stage: partner indices (lo, lo + j)
+                const int lo = ((t / j) * (j << 1)) + (t % j);
+                const int hiI = lo + j;
+                const bool asc = ((lo & k) == 0);
+                const unsigned long long a = skey[lo], b = skey[hiI];
+                if ((a > b) == asc) {
+                    skey[lo] = b;
+                    skey[hiI] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const int k = (int)(unsigned)(skey[i] & 0xffffffffull);
+        const int g = gaussian_ids[k];
+        const GsbRecord r = make_record(__ldg(xys + g), __ldg(conics + 3 * g), __ldg(conics + 3 * g + 1),
+                                        __ldg(conics + 3 * g + 2), __ldg(opacities + g), __ldg(colors + 3 * g),
+                                        __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), k);
+        float4 *dst = reinterpret_cast<float4 *>(records + range.x + i);
+        stg_stream4(dst, r.q0);
+        stg_stream4(dst + 1, r.q1);
+        stg_stream4(dst + 2, r.q2);
+        if (sorted_index) sorted_index[range.x + i] = k;
+        if (gaussian_ids_sorted) gaussian_ids_sorted[range.x + i] = g;
+    }
+}
+
+struct BucketLayout {
+    size_t comp, gids, total;
+};
+BucketLayout bucket_layout(int m) {
+    BucketLayout L;
+    size_t o = 0;
+    L.comp = o; o += gsb_align_up((size_t)m * 8, 256);
+    L.gids = o; o += gsb_align_up((size_t)m * 4, 256);
+    L.total = o;
+    return L;
+}
+
+constexpr int BUCKET_MAX_CAP = 16384;  // 128 KB of shared memory per CTA
+
+}  // namespace
+
+extern "C" int gsb_bucket_max_tile_len(void) { return BUCKET_MAX_CAP; }
+
+extern "C" size_t gsb_bucket_workspace_bytes(int m) { return bucket_layout(m > 0 ? m : 0).total + 256; }
+
+// Phase 1 (before the M read-back): tile sizes -> tile_bins, tile_cursor [tiles] (write cursors for phase 2),
+// stats = {M, max tile length} (device int32[2]).
+extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
+                                      int32_t *tile_bins, int32_t *tile_cursor, int32_t *stats,
+                                      gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && tiles_x > 0 && tiles_y > 0 && tile_bins && tile_cursor && stats);
+    const int T = tiles_x * tiles_y;
+    cudaStream_t s = (cudaStream_t)stream;
+    GSB_CUDA(cudaMemsetAsync(tile_cursor, 0, (size_t)T * 4, s));
+    if (n > 0) {
+        GSB_CHECK_ARG(xys && radii && ((uintptr_t)xys % 8) == 0);
+        tile_count_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, reinterpret_cast<const float2 *>(xys), radii,
+                                                            tiles_x, tiles_y, tile_cursor);
+    }
+    tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_cursor, reinterpret_cast<int2 *>(tile_bins), stats);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Phase 2 (after the read-back of {M, max_len}): bucket emit + per-tile sort + record pack.  Consumes
+// (advances) tile_cursor.  sorted_index / gaussian_ids_sorted are optional outputs ([m] int32, may be NULL).
+extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float *xys, const float *depths,
+                                    const int32_t *radii, const int32_t *cum_tiles_hit, int tiles_x,
+                                    int tiles_y, const int32_t *tile_bins, int32_t *tile_cursor,
+                                    const float *conics, const float *colors, const float *opacities,
+                                    void *workspace, size_t workspace_bytes, void *records,
+                                    int32_t *sorted_index, int32_t *gaussian_ids_sorted, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && m >= 0 && tiles_x > 0 && tiles_y > 0 && max_tile_len >= 0);
+    if (n == 0 || m == 0) return 0;
+    GSB_CHECK_ARG(xys && depths && radii && cum_tiles_hit && tile_bins && tile_cursor && conics && colors &&
+                  opacities && workspace && records);
+    GSB_CHECK_ARG(((uintptr_t)workspace % 256) == 0 && ((uintptr_t)records % 16) == 0);
+    const int T = tiles_x * tiles_y;
+    const BucketLayout L = bucket_layout(m);
+    if (workspace_bytes < L.total) {
+        gsb_set_error(GSB_ERR_WORKSPACE, "bucket workspace too small", __FILE__, __LINE__);
+        return GSB_ERR_WORKSPACE;
+    }
+    int cap = 32;
+    while (cap < max_tile_len) cap <<= 1;
+    if (cap > BUCKET_MAX_CAP) {
+        gsb_set_error(GSB_ERR_UNSUPPORTED, "tile list longer than the in-shared-memory sort capacity; "
+                      "use the generic gsb_sort_intersects path", __FILE__, __LINE__);
+        return GSB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    unsigned long long *comp = (unsigned long long *)(ws + L.comp);
+    int *gids = (int *)(ws + L.gids);
+    bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, reinterpret_cast<const float2 *>(xys), depths, radii,
+                                                         cum_tiles_hit, tiles_x, tiles_y, tile_cursor, comp, gids);
+    const size_t smem = (size_t)cap * 8;
+    if (smem > 48 * 1024)
+        GSB_CUDA(cudaFuncSetAttribute(tile_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tile_sort_pack_kernel<<<T, 256, smem, s>>>(cap, reinterpret_cast<const int2 *>(tile_bins), comp, gids,
+                                              reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
+                                              reinterpret_cast<GsbRecord *>(records), sorted_index,
+                                              gaussian_ids_sorted);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}

@@ -67,35 +67,66 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
     torch::Tensor x = gsb::f32(xys), con = gsb::f32(conics), col = gsb::f32(colors), op = gsb::f32(opacity);
     torch::Tensor bg = gsb::f32(background), nth = gsb::i32(numTilesHit);
 
-    // inclusive scan + the path's single device->host read-back (rasterize_gaussians.cpp:62-63)
+    // inclusive scan (slot offsets of the gradient rows) ...
     torch::Tensor cum = torch::empty({n}, gsb::like(x, torch::kInt32));
-    int numIntersects = 0;
+    torch::Tensor d = gsb::f32(depths), r = gsb::i32(radii);
+    const int numTiles = tilesX * tilesY;
+    torch::Tensor tileBins = torch::empty({numTiles, 2}, gsb::like(x, torch::kInt32));
+    torch::Tensor stats = torch::zeros({2}, gsb::like(x, torch::kInt32));
+    torch::Tensor tileCursor = torch::empty({numTiles}, gsb::like(x, torch::kInt32));
     if (n > 0) {
         const size_t sb = gsb_cumsum_workspace_bytes(n);
         torch::Tensor sws = torch::empty({(int64_t)sb}, gsb::like(x, torch::kUInt8));
         gsb::check(gsb_cumsum_tiles_hit(n, nth.data_ptr<int32_t>(), cum.data_ptr<int32_t>(), sws.data_ptr(), sb,
                                         nullptr, gsb::stream()),
                    "gsb_cumsum_tiles_hit");
-        numIntersects = cum[n - 1].item<int>();
     }
-    const int m = numIntersects;
-    Binned b = bin_and_sort(n, m, x, depths, radii, cum, tileBounds);
+    // ... tile sizes -> tile_bins, and the path's single device->host read-back (rasterize_gaussians.cpp:63):
+    // M together with the longest tile list
+    gsb::check(gsb_bucket_tile_ranges(n, gsb::fp(x), r.data_ptr<int32_t>(), tilesX, tilesY,
+                                      tileBins.data_ptr<int32_t>(), tileCursor.data_ptr<int32_t>(),
+                                      stats.data_ptr<int32_t>(), gsb::stream()),
+               "gsb_bucket_tile_ranges");
+    torch::Tensor statsHost = stats.cpu();
+    const int m = statsHost[0].item<int>(), maxLen = statsHost[1].item<int>();
 
     torch::Tensor records = torch::empty({(int64_t)gsb_raster_records_bytes(m)}, gsb::like(x, torch::kUInt8));
     torch::Tensor outImg = torch::empty({imgHeight, imgWidth, 3}, gsb::like(x, torch::kFloat32));
     torch::Tensor finalTs = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kFloat32));
     torch::Tensor finalIdx = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kInt32));
-    gsb::check(gsb_rasterize_forward(imgHeight, imgWidth, tilesX, tilesY, m,
-                                     b.gaussianIdsSorted.data_ptr<int32_t>(), b.sortedIndex.data_ptr<int32_t>(),
-                                     b.tileBins.data_ptr<int32_t>(), gsb::fp(x), gsb::fp(con), gsb::fp(col),
-                                     gsb::fp(op), gsb::fp(bg), records.data_ptr(), gsb::fpw(outImg),
-                                     gsb::fpw(finalTs), finalIdx.data_ptr<int32_t>(), gsb::stream()),
-               "gsb_rasterize_forward");
+    if (maxLen <= gsb_bucket_max_tile_len()) {
+        // fast path: two-level bucket sort fused with the record packing
+        const size_t wsBytes = gsb_bucket_workspace_bytes(m);
+        torch::Tensor ws = torch::empty({(int64_t)wsBytes + 256}, gsb::like(x, torch::kUInt8));
+        char *wp = (char *)ws.data_ptr();
+        wp += (256 - ((uintptr_t)wp % 256)) % 256;
+        gsb::check(gsb_bucket_sort_pack(n, m, maxLen, gsb::fp(x), gsb::fp(d), r.data_ptr<int32_t>(),
+                                        cum.data_ptr<int32_t>(), tilesX, tilesY, tileBins.data_ptr<int32_t>(),
+                                        tileCursor.data_ptr<int32_t>(), gsb::fp(con), gsb::fp(col), gsb::fp(op), wp, wsBytes, records.data_ptr(),
+                                        nullptr, nullptr, gsb::stream()),
+                   "gsb_bucket_sort_pack");
+        gsb::check(gsb_rasterize_forward_packed(imgHeight, imgWidth, tilesX, tilesY, m,
+                                                tileBins.data_ptr<int32_t>(), gsb::fp(bg), records.data_ptr(),
+                                                gsb::fpw(outImg), gsb::fpw(finalTs), finalIdx.data_ptr<int32_t>(),
+                                                gsb::stream()),
+                   "gsb_rasterize_forward_packed");
+    } else {
+        // pathological tile lists: generic global radix sort
+        Binned b = bin_and_sort(n, m, x, d, r, cum, tileBounds);
+        tileBins = b.tileBins;
+        gsb::check(gsb_rasterize_forward(imgHeight, imgWidth, tilesX, tilesY, m,
+                                         b.gaussianIdsSorted.data_ptr<int32_t>(),
+                                         b.sortedIndex.data_ptr<int32_t>(), b.tileBins.data_ptr<int32_t>(),
+                                         gsb::fp(x), gsb::fp(con), gsb::fp(col), gsb::fp(op), gsb::fp(bg),
+                                         records.data_ptr(), gsb::fpw(outImg), gsb::fpw(finalTs),
+                                         finalIdx.data_ptr<int32_t>(), gsb::stream()),
+                   "gsb_rasterize_forward");
+    }
 
     ctx->saved_data["imgWidth"] = imgWidth;
     ctx->saved_data["imgHeight"] = imgHeight;
     ctx->saved_data["numIntersects"] = m;
-    ctx->save_for_backward({b.tileBins, con, op, records, cum, bg, finalTs, finalIdx});
+    ctx->save_for_backward({tileBins, con, op, records, cum, bg, finalTs, finalIdx});
     return outImg;
 }
 

@@ -48,6 +48,26 @@ struct __align__(128) WarpRing {
 };
 
 #ifdef __CUDACC__
+// Builds the 48-B record of one intersection from the per-Gaussian attributes (see layout above).
+__device__ __forceinline__ GsbRecord make_record(float2 xy, float a, float b, float c, float opac, float r,
+                                                 float g, float bl, int k) {
+    const float lo = (opac > 0.f) ? log2f(opac) : -INFINITY;
+    // extent of {sigma <= smax}: conservative (x1.001 + 0.01 px); no culling for degenerate conics
+    const float smax = fmaxf(0.f, fmaf(lo, GSB_LN2, GSB_SMAX_BIAS));
+    const float det = a * c - b * b;
+    float hx = INFINITY, hy = INFINITY;
+    if (det > 0.f && a > 0.f && c > 0.f) {
+        const float s2 = 2.f * smax / det;
+        hx = sqrtf(s2 * c) * 1.001f + 0.01f;
+        hy = sqrtf(s2 * a) * 1.001f + 0.01f;
+    }
+    GsbRecord rec;
+    rec.q0 = make_float4(xy.x, xy.y, lo, __int_as_float(k));
+    rec.q1 = make_float4(0.5f * a, b, 0.5f * c, hx);
+    rec.q2 = make_float4(r, g, bl, hy);
+    return rec;
+}
+
 // Per-lane cull of record `lane` of a chunk against this warp's tile: returns the 8-bit mask of slots
 // (row pairs) whose rows intersect the record's y-extent, or 0 if the record cannot touch the tile.
 __device__ __forceinline__ unsigned record_slot_mask(const GsbRecord &r, float tile_x0, float tile_y0) {

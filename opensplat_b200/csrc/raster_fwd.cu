@@ -34,23 +34,9 @@ pack_records_kernel(int m, const int *__restrict__ gaussian_ids_sorted,
     if (i >= m) return;
     const int g = gaussian_ids_sorted[i];
     const int k = sorted_index ? sorted_index[i] : i;
-    const float2 xy = __ldg(xys + g);
-    const float a = __ldg(conics + 3 * g), b = __ldg(conics + 3 * g + 1), c = __ldg(conics + 3 * g + 2);
-    const float opac = __ldg(opacities + g);
-    const float lo = (opac > 0.f) ? log2f(opac) : -INFINITY;
-    // extent of {sigma <= smax}: conservative (x1.001 + 0.01 px); no culling for degenerate conics
-    const float smax = fmaxf(0.f, fmaf(lo, GSB_LN2, GSB_SMAX_BIAS));
-    const float det = a * c - b * b;
-    float hx = INFINITY, hy = INFINITY;
-    if (det > 0.f && a > 0.f && c > 0.f) {
-        const float s2 = 2.f * smax / det;
-        hx = sqrtf(s2 * c) * 1.001f + 0.01f;
-        hy = sqrtf(s2 * a) * 1.001f + 0.01f;
-    }
-    GsbRecord r;
-    r.q0 = make_float4(xy.x, xy.y, lo, __int_as_float(k));
-    r.q1 = make_float4(0.5f * a, b, 0.5f * c, hx);
-    r.q2 = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), hy);
+    const GsbRecord r = make_record(__ldg(xys + g), __ldg(conics + 3 * g), __ldg(conics + 3 * g + 1),
+                                    __ldg(conics + 3 * g + 2), __ldg(opacities + g), __ldg(colors + 3 * g),
+                                    __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), k);
     float4 *dst = reinterpret_cast<float4 *>(records + i);
     stg_stream4(dst, r.q0);
     stg_stream4(dst + 1, r.q1);
@@ -218,6 +204,27 @@ extern "C" int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tile
             m, gaussian_ids_sorted, sorted_index, reinterpret_cast<const float2 *>(xys), conics, colors,
             opacities, reinterpret_cast<GsbRecord *>(records));
     }
+    unsigned *counters = reinterpret_cast<unsigned *>(
+        reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
+    GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
+    const int num_tiles = tiles_x * tiles_y;
+    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel, num_tiles);
+    rasterize_forward_kernel<<<grid, RK_THREADS, 0, s>>>(
+        img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, int tiles_y, int m,
+                                            const int32_t *tile_bins, const float *background,
+                                            void *records, float *out_img, float *final_Ts,
+                                            int32_t *final_idx, gsb_stream_t stream) {
+    GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0);
+    GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
+    GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx && records);
+    GSB_CHECK_ARG(((uintptr_t)records % 16) == 0);
+    cudaStream_t s = (cudaStream_t)stream;
     unsigned *counters = reinterpret_cast<unsigned *>(
         reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
     GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));

@@ -181,6 +181,49 @@ def binAndSortGaussians(numPoints, numIntersects, xys, depths, radii, cumTilesHi
     return isect, gids, ks, gs, bins
 
 
+def bucket_tile_ranges(xys, radii, tile_bounds_):
+    """Fast-path phase 1: tile_bins [T,2], the per-tile write cursors for phase 2, and
+    stats = (M, longest tile list), without sorting."""
+    n = xys.shape[0]
+    T = tile_bounds_[0] * tile_bounds_[1]
+    bins = _empty((T, 2), torch.int32, xys)
+    cursor = _empty((T,), torch.int32, xys)
+    stats = _empty((2,), torch.int32, xys)
+    capi.check(capi.lib().gsb_bucket_tile_ranges(n, capi.ptr(capi.f32(xys)), capi.ptr(radii.contiguous()),
+                                                 tile_bounds_[0], tile_bounds_[1], capi.ptr(bins), capi.ptr(cursor),
+                                                 capi.ptr(stats), capi.stream()))
+    return bins, cursor, stats
+
+
+def bucket_sort_pack(n, m, max_tile_len, xys, depths, radii, cum_tiles_hit, tile_bounds_, tile_bins, tile_cursor,
+                     conics, colors, opacities, want_index=False):
+    """Fast-path phase 2: bucket emit + per-tile shared-memory sort + record pack -> records (+ optional
+    sorted_index / gaussian_ids_sorted for inspection).  Consumes tile_cursor."""
+    L = capi.lib()
+    ws = _ws.get(xys.device, "bucket", L.gsb_bucket_workspace_bytes(m) + 256)
+    off = (-ws.data_ptr()) % 256
+    records = torch.empty(L.gsb_raster_records_bytes(m), dtype=torch.uint8, device=xys.device)
+    idx = _empty((m,), torch.int32, xys) if want_index else None
+    gs = _empty((m,), torch.int32, xys) if want_index else None
+    capi.check(L.gsb_bucket_sort_pack(
+        n, m, max_tile_len, capi.ptr(capi.f32(xys)), capi.ptr(capi.f32(depths)), capi.ptr(radii.contiguous()),
+        capi.ptr(cum_tiles_hit), tile_bounds_[0], tile_bounds_[1], capi.ptr(tile_bins), capi.ptr(tile_cursor),
+        capi.ptr(capi.f32(conics)), capi.ptr(capi.f32(colors)), capi.ptr(capi.f32(opacities)), ws.data_ptr() + off,
+        ws.numel() - off, capi.ptr(records), capi.ptr(idx), capi.ptr(gs), capi.stream()))
+    return records, idx, gs
+
+
+def rasterize_forward_packed(tile_bounds_, img_size, m, tile_bins, records, background):
+    W, H = img_size[0], img_size[1]
+    out = _empty((H, W, 3), torch.float32, records)
+    fT = _empty((H, W), torch.float32, records)
+    fI = _empty((H, W), torch.int32, records)
+    capi.check(capi.lib().gsb_rasterize_forward_packed(
+        H, W, tile_bounds_[0], tile_bounds_[1], m, capi.ptr(tile_bins), capi.ptr(capi.f32(background)),
+        capi.ptr(records), capi.ptr(out), capi.ptr(fT), capi.ptr(fI), capi.stream()))
+    return out, fT, fI
+
+
 def rasterize_forward(tile_bounds_, img_size, gaussian_ids_sorted, sorted_index, tile_bins, xys, conics,
                       colors, opacities, background):
     W, H = img_size[0], img_size[1]
@@ -256,13 +299,22 @@ class RasterizeGaussians(torch.autograd.Function):
     def forward(ctx, xys, depths, radii, conics, numTilesHit, colors, opacity, imgHeight, imgWidth, background):
         numPoints = xys.shape[0]
         tb = tile_bounds(imgWidth, imgHeight)
+        if colors.shape[-1] != 3:
+            raise ValueError("only 3-channel colors are supported")
         cum = cumsum_tiles_hit(numTilesHit)
-        # the one device->host read-back of the path (rasterize_gaussians.cpp:63)
-        numIntersects = int(cum[-1].item()) if numPoints > 0 else 0
-        _, _, _, gs, bins, idx = binAndSortGaussians(numPoints, numIntersects, xys, depths, radii, cum, tb,
-                                                     return_index=True)
-        out, fT, fI, records = rasterize_forward(tb, (imgWidth, imgHeight, 1), gs, idx, bins, xys, conics,
-                                                 colors, opacity, background)
+        bins, cursor, stats = bucket_tile_ranges(xys, radii, tb)
+        # the one device->host read-back of the path (rasterize_gaussians.cpp:63): M and the longest tile list
+        numIntersects, max_len = (int(v) for v in stats.tolist())
+        if max_len <= capi.lib().gsb_bucket_max_tile_len():
+            records, _, _ = bucket_sort_pack(numPoints, numIntersects, max_len, xys, depths, radii, cum, tb, bins,
+                                             cursor, conics, colors, opacity)
+            out, fT, fI = rasterize_forward_packed(tb, (imgWidth, imgHeight, 1), numIntersects, bins, records,
+                                                   background)
+        else:  # pathological tile lists: generic global radix sort (binAndSortGaussians)
+            _, _, _, gs, bins, idx = binAndSortGaussians(numPoints, numIntersects, xys, depths, radii, cum, tb,
+                                                         return_index=True)
+            out, fT, fI, records = rasterize_forward(tb, (imgWidth, imgHeight, 1), gs, idx, bins, xys, conics,
+                                                     colors, opacity, background)
         ctx.meta = (int(imgHeight), int(imgWidth), numPoints, numIntersects)
         ctx.save_for_backward(bins, conics, opacity, records, cum, background, fT, fI)
         return out

@@ -17,7 +17,9 @@ from .ops import tile_bounds, num_sh_bases
 
 
 class SplatPipeline:
-    def __init__(self, n, W, H, sh_degree=3, device="cuda:0", m_capacity=None, stage_timing=False):
+    def __init__(self, n, W, H, sh_degree=3, device="cuda:0", m_capacity=None, stage_timing=False,
+                 binning="bucket"):
+        self.binning = binning  # "bucket" (two-level, fused pack) or "radix" (generic global sort)
         self.n, self.W, self.H, self.deg = int(n), int(W), int(H), int(sh_degree)
         self.K = num_sh_bases(sh_degree)
         self.dev = torch.device(device)
@@ -56,8 +58,9 @@ class SplatPipeline:
         self.v_conic = torch.empty((n, 3), dtype=f32, device=d)
         self.v_rgbs = torch.empty((n, 3), dtype=f32, device=d)
         self.scan_ws = torch.empty(self.L.gsb_cumsum_workspace_bytes(n), dtype=torch.uint8, device=d)
-        self.total_dev = torch.zeros(1, dtype=i32, device=d)
-        self.total_host = torch.zeros(1, dtype=i32).pin_memory()
+        self.total_dev = torch.zeros(2, dtype=i32, device=d)
+        self.total_host = torch.zeros(2, dtype=i32).pin_memory()
+        self.max_len = 0
         # ---- per-pixel ----
         self.out_img = torch.empty((H, W, 3), dtype=f32, device=d)
         self.final_Ts = torch.empty((H, W), dtype=f32, device=d)
@@ -67,6 +70,7 @@ class SplatPipeline:
         self.background = torch.zeros(3, dtype=f32, device=d)
         self.loss = torch.zeros(1, dtype=f32, device=d)
         self.tile_bins = torch.empty((self.T, 2), dtype=i32, device=d)
+        self.tile_cursor = torch.empty((self.T,), dtype=i32, device=d)
         # ---- camera ----
         self.viewmat = torch.eye(4, dtype=f32, device=d)
         self.projmat = torch.eye(4, dtype=f32, device=d)
@@ -93,6 +97,7 @@ class SplatPipeline:
         self.sort_ws = torch.empty(self.L.gsb_sort_workspace_bytes(cap) + 256, dtype=torch.uint8, device=d)
         self.records = torch.empty(self.L.gsb_raster_records_bytes(cap), dtype=torch.uint8, device=d)
         self.grad_rows = torch.empty(self.L.gsb_raster_grad_rows_bytes(cap), dtype=torch.uint8, device=d)
+        self.bucket_ws = torch.empty(self.L.gsb_bucket_workspace_bytes(cap) + 256, dtype=torch.uint8, device=d)
         self.m_cap = cap
 
     def load_scene(self, sc):
@@ -146,28 +151,49 @@ class SplatPipeline:
         self._stage("scan")
         capi.check(L.gsb_cumsum_tiles_hit(n, P(self.nth), P(self.cum), P(self.scan_ws), self.scan_ws.numel(),
                                           P(self.total_dev), s))
-        # the path's one device->host read-back (rasterize_gaussians.cpp:63)
+        use_bucket = self.binning == "bucket"
+        if use_bucket:
+            capi.check(L.gsb_bucket_tile_ranges(n, P(self.xys), P(self.radii), self.tb[0], self.tb[1],
+                                                P(self.tile_bins), P(self.tile_cursor), P(self.total_dev), s))
+        # the path's one device->host read-back (rasterize_gaussians.cpp:63): M (+ longest tile list)
         self.total_host.copy_(self.total_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         m = int(self.total_host[0])
+        self.max_len = int(self.total_host[1]) if use_bucket else 0
         self.m = m
         if m > self.m_cap:
             self._grow(m)
-        self._stage("emit")
-        capi.check(L.gsb_map_gaussian_to_intersects(n, m, P(self.xys), P(self.depths), P(self.radii), P(self.cum),
-                                                    self.tb[0], self.tb[1], P(self.isect), P(self.gids), s))
-        self._stage("sort")
-        off = (-self.sort_ws.data_ptr()) % 256
-        capi.check(L.gsb_sort_intersects(m, self.T, P(self.isect), P(self.isect_sorted), P(self.sorted_index),
-                                         self.sort_ws.data_ptr() + off, self.sort_ws.numel() - off, s))
-        self._stage("bins")
-        capi.check(L.gsb_gather_bin_edges(m, self.T, P(self.isect_sorted), P(self.sorted_index), P(self.gids),
-                                          P(self.gids_sorted), P(self.tile_bins), s))
-        self._stage("raster_fwd")
-        capi.check(L.gsb_rasterize_forward(H, W, self.tb[0], self.tb[1], m, P(self.gids_sorted),
-                                           P(self.sorted_index), P(self.tile_bins), P(self.xys), P(self.conics),
-                                           P(self.rgbs), P(p["opacities"]), P(self.background), P(self.records),
-                                           P(self.out_img), P(self.final_Ts), P(self.final_idx), s))
+        if use_bucket and self.max_len > L.gsb_bucket_max_tile_len():
+            use_bucket = False
+        if use_bucket:
+            self._stage("bucket_sort_pack")
+            boff = (-self.bucket_ws.data_ptr()) % 256
+            capi.check(L.gsb_bucket_sort_pack(n, m, self.max_len, P(self.xys), P(self.depths), P(self.radii),
+                                              P(self.cum), self.tb[0], self.tb[1], P(self.tile_bins),
+                                              P(self.tile_cursor), P(self.conics), P(self.rgbs), P(p["opacities"]),
+                                              self.bucket_ws.data_ptr() + boff,
+                                              self.bucket_ws.numel() - boff, P(self.records), None, None, s))
+            self._stage("raster_fwd")
+            capi.check(L.gsb_rasterize_forward_packed(H, W, self.tb[0], self.tb[1], m, P(self.tile_bins),
+                                                      P(self.background), P(self.records), P(self.out_img),
+                                                      P(self.final_Ts), P(self.final_idx), s))
+        else:
+            self._stage("emit")
+            capi.check(L.gsb_map_gaussian_to_intersects(n, m, P(self.xys), P(self.depths), P(self.radii),
+                                                        P(self.cum), self.tb[0], self.tb[1], P(self.isect),
+                                                        P(self.gids), s))
+            self._stage("sort")
+            off = (-self.sort_ws.data_ptr()) % 256
+            capi.check(L.gsb_sort_intersects(m, self.T, P(self.isect), P(self.isect_sorted), P(self.sorted_index),
+                                             self.sort_ws.data_ptr() + off, self.sort_ws.numel() - off, s))
+            self._stage("bins")
+            capi.check(L.gsb_gather_bin_edges(m, self.T, P(self.isect_sorted), P(self.sorted_index), P(self.gids),
+                                              P(self.gids_sorted), P(self.tile_bins), s))
+            self._stage("raster_fwd")
+            capi.check(L.gsb_rasterize_forward(H, W, self.tb[0], self.tb[1], m, P(self.gids_sorted),
+                                               P(self.sorted_index), P(self.tile_bins), P(self.xys), P(self.conics),
+                                               P(self.rgbs), P(p["opacities"]), P(self.background), P(self.records),
+                                               P(self.out_img), P(self.final_Ts), P(self.final_idx), s))
         self._stage("end_fwd")
         return self.out_img
 

@@ -1,0 +1,58 @@
+"""CPU, world_size 2, gloo: host logic of the data-parallel path (flat gradient bucket, view sharding,
+one all-reduce per step, replicas stay identical after the same update)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from opensplat_b200 import parallel
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, K = 257, 16
+    offs, total = parallel.flat_layout(n, K)
+    assert total == n * 59
+    torch.manual_seed(0)                      # same replica everywhere
+    param = torch.randn(total)
+    grad = torch.zeros(total)
+    g = parallel.flat_views(grad, offs)
+    p = parallel.flat_views(param, offs)
+    assert p["coeffs"].data_ptr() == param[offs["coeffs"][0]:].data_ptr()   # views alias the flat buffer
+    # every rank renders different views -> different local gradients
+    my_views = parallel.views_for_rank(8, rank, world)
+    for name in g:
+        g[name].fill_(0)
+        for v in my_views:
+            g[name].add_(float(v + 1))
+    parallel.allreduce_gradients(grad, world, average=False)
+    expect = float(sum(v + 1 for v in range(8)))
+    ok = bool(torch.all(grad == expect))
+    param.add_(grad, alpha=-0.01)             # identical update on every rank
+    ok = ok and parallel.replicas_in_sync(param, world)
+    # a rank that diverges is detected
+    if rank == 1:
+        param[3] += 1.0
+    diverged = not parallel.replicas_in_sync(param, world)
+    ret[rank] = (ok, diverged, my_views)
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] and ret[1][0]
+    assert ret[0][1] and ret[1][1]
+    assert ret[0][2] == [0, 2, 4, 6] and ret[1][2] == [1, 3, 5, 7]
+
+
+def test_view_sharding_covers_all_views_once():
+    for world in (1, 2, 4, 8):
+        seen = sorted(v for r in range(world) for v in parallel.views_for_rank(8, r, world))
+        assert seen == list(range(8))

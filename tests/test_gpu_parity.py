@@ -109,6 +109,36 @@ def test_binning_bit_exact(n, W, H, scale):
     assert np.array_equal(npy(bins), ob["tile_bins"])
 
 
+@pytest.mark.parametrize("n,W,H,scale", [(4000, 256, 256, 0.3), (30000, 640, 360, 0.15), (50, 48, 40, 2.0),
+                                         (200_000, 1024, 576, 0.05)])
+def test_bucket_binning_matches_generic_sort(n, W, H, scale):
+    """The two-level fast path (tile bucket + in-smem depth sort + fused pack) must give the same tile_bins
+    and the same per-tile order as emit + global 64-bit sort + bin edges (bit-exact), and the same records."""
+    sc = _scene(n, W, H, scale, seed=3 * n)
+    if n == 4000:   # duplicate depths: ties must resolve to ascending unsorted slot (stable order)
+        sc["means"][:, 2] = np.round(sc["means"][:, 2] * 8) / 8
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    cum = ops.cumsum_tiles_hit(nth)
+    tb = ops.tile_bounds(W, H)
+    rng = np.random.default_rng(5)
+    colors = cu(rng.uniform(0, 1, (n, 3)).astype(np.float32))
+    opac = cu(sc["opacities"])
+    bins_b, cursor, stats = ops.bucket_tile_ranges(xys, radii, tb)
+    m, max_len = (int(v) for v in stats.tolist())
+    assert m == int(cum[-1])
+    rec_b, idx_b, gs_b = ops.bucket_sort_pack(n, m, max_len, xys, depths, radii, cum, tb, bins_b, cursor, conics, colors, opac,
+                                              want_index=True)
+    isect, gids, ks, gs, bins, idx = ops.binAndSortGaussians(n, m, xys, depths, radii, cum, tb, return_index=True)
+    assert torch.equal(bins_b, bins)
+    assert int((bins[:, 1] - bins[:, 0]).max()) == max_len
+    assert torch.equal(idx_b, idx) and torch.equal(gs_b, gs)
+    bg = cu(np.zeros(3, np.float32))
+    out, fT, fI, rec = ops.rasterize_forward(tb, (W, H, 1), gs, idx, bins, xys, conics, colors, opac, bg)
+    assert torch.equal(rec_b[: m * 48], rec[: m * 48])
+    out_b, fT_b, fI_b = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins_b, rec_b, bg)
+    assert torch.equal(out, out_b) and torch.equal(fI, fI_b)
+
+
 def test_sort_stability_with_duplicate_keys():
     # many identical (tile, depth) keys: the permutation must be the stable one
     rng = np.random.default_rng(0)
