@@ -58,6 +58,13 @@ int gsb_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs,
 int gsb_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *v_colors,
                     float *v_coeffs, gsb_stream_t stream);
 
+/* Fused variants (optional): rgbs = clamp_min(SH(coeffs) + bias, 0) in one pass -- the
+ * glue of model.cpp:188-192 -- and its VJP v_coeffs = Y (x) (v_rgbs * [rgbs > 0]). */
+int gsb_sh_forward_rgb(int n, int degree, int degrees_to_use, const float *viewdirs, const float *coeffs,
+                       float bias, float *rgbs, gsb_stream_t stream);
+int gsb_sh_backward_rgb(int n, int degree, int degrees_to_use, const float *viewdirs, const float *rgbs,
+                        const float *v_rgbs, float *v_coeffs, gsb_stream_t stream);
+
 /* ---- Projection ------------------------------------------------------------------------------
  * gsb_project_forward replaces project_gaussians_forward_tensor (bindings.h:42-65,
  *   bindings.cu:133-207, kernel forward.cu:19-103).  Outputs cov3d [n,6], xys [n,2], depths [n]
@@ -166,8 +173,8 @@ int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int tiles_y, int n
                            float *v_colors, float *v_opacity, gsb_stream_t stream);
 
 /* ---- Streaming helpers around the path (SURVEY.md 8f "next" rows) ------------------------------
- * gsb_mse_loss_grad: loss = mean((img-target)^2) accumulated into *loss_out (device float, caller
- *   zeroes it) and v_img = 2 (img-target) * inv_count, one pass (simple_trainer.cpp:199-201:
+ * gsb_mse_loss_grad: loss = mean((img-target)^2) written to *loss_out (device float; zeroed by the
+ *   call, then accumulated) and v_img = 2 (img-target) * inv_count, one pass (simple_trainer.cpp:199-201:
  *   torch::nn::MSELoss + autograd).  n = number of floats, inv_count = 1/n.
  * gsb_adam_step: fused Adam over a flat fp32 buffer, semantics of torch::optim::Adam without weight
  *   decay / amsgrad (simple_trainer.cpp:146,202; model.cpp:236-243): bias_correction{1,2} = 1 - beta^t. */

@@ -19,6 +19,8 @@ _SIGS = {
     "gsb_last_error": (C.c_char_p, []),
     "gsb_sh_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "gsb_sh_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gsb_sh_forward_rgb": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp]),
+    "gsb_sh_backward_rgb": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "gsb_project_forward": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _f,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_project_backward": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i,

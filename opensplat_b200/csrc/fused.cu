@@ -79,7 +79,7 @@ int sm_count() {
 
 }  // namespace
 
-// loss_out (device float) is accumulated into: the caller zeroes it (or passes a zeroed slot).
+// loss_out (device float) is zeroed here (stream-ordered) and then accumulated into by the kernel.
 extern "C" int gsb_mse_loss_grad(long long n, const float *img, const float *target, float *v_img,
                                  float *loss_out, float inv_count, gsb_stream_t stream) {
     GSB_CHECK_ARG(n >= 0);
@@ -87,6 +87,7 @@ extern "C" int gsb_mse_loss_grad(long long n, const float *img, const float *tar
     GSB_CHECK_ARG(img && target && v_img && loss_out);
     const bool vec = (((uintptr_t)img | (uintptr_t)target | (uintptr_t)v_img) % 16) == 0;
     const long long n4 = vec ? n / 4 : 0;
+    GSB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), (cudaStream_t)stream));
     mse_loss_grad_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(n4, n, img, target, v_img, loss_out,
                                                                         inv_count);
     GSB_LAUNCH_CHECK();

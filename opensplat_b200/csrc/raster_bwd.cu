@@ -149,37 +149,50 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f;  // sum w, sum w dy, sum w dy^2 over this lane's pixels
                 float a_r = 0.f, a_g = 0.f, a_b = 0.f;
                 bool any = false;
-#pragma unroll
-                for (int j = 0; j < RK_PIX; ++j) {
-                    if (!((rm >> j) & 1u)) continue;                          // warp-uniform
-                    const float dy = q0.y - py[j];
-                    const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
-                    if (__float_as_uint(sigma) > __float_as_uint(smax)) continue;  // !(0 <= sigma <= smax)
-                    const float au = ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z));   // opac * exp(-sigma)
-                    const float alpha = fminf(0.99f, au);
-                    if (idx <= binf[j] && alpha >= (1.f / 255.f)) {
-                        any = true;
-                        const float ra = rcp_approx(1.f - alpha);
-                        T[j] *= ra;
-                        const float fac = alpha * T[j];
-                        a_r = fmaf(fac, vor[j], a_r);
-                        a_g = fmaf(fac, vog[j], a_g);
-                        a_b = fmaf(fac, vob[j], a_b);
-                        float v_alpha = (q2.x * T[j] - bufr[j] * ra) * vor[j];
-                        v_alpha = fmaf(q2.y * T[j] - bufg[j] * ra, vog[j], v_alpha);
-                        v_alpha = fmaf(q2.z * T[j] - bufb[j] * ra, vob[j], v_alpha);
-                        v_alpha = fmaf(ra, q[j], v_alpha);
-                        bufr[j] = fmaf(q2.x, fac, bufr[j]);
-                        bufg[j] = fmaf(q2.y, fac, bufg[j]);
-                        bufb[j] = fmaf(q2.z, fac, bufb[j]);
-                        // v_sigma = -opac*vis*v_alpha = -w (backward.cu:323); v_opacity += vis*v_alpha = w/opac
-                        const float w = au * v_alpha;
-                        const float wdy = w * dy;
-                        s0 += w;
-                        s1 += wdy;
-                        s2 = fmaf(wdy, dy, s2);
-                    }
+                const int jlo = __ffs(rm) - 1, jhi = 31 - __clz(rm);   // slots inside the y-extent (contiguous)
+#define GSB_BWD_SLOT(j)                                                                                   \
+    {                                                                                                     \
+        const float dy = q0.y - py[j];                                                                    \
+        const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);                                          \
+        if (__float_as_uint(sigma) <= __float_as_uint(smax)) { /* 0 <= sigma <= smax */                   \
+            const float au = ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z)); /* opac * exp(-sigma) */          \
+            const float alpha = fminf(0.99f, au);                                                         \
+            if (idx <= binf[j] && alpha >= (1.f / 255.f)) {                                               \
+                any = true;                                                                               \
+                const float ra = rcp_approx(1.f - alpha);                                                 \
+                T[j] *= ra;                                                                               \
+                const float fac = alpha * T[j];                                                           \
+                a_r = fmaf(fac, vor[j], a_r);                                                             \
+                a_g = fmaf(fac, vog[j], a_g);                                                             \
+                a_b = fmaf(fac, vob[j], a_b);                                                             \
+                float v_alpha = (q2.x * T[j] - bufr[j] * ra) * vor[j];                                    \
+                v_alpha = fmaf(q2.y * T[j] - bufg[j] * ra, vog[j], v_alpha);                              \
+                v_alpha = fmaf(q2.z * T[j] - bufb[j] * ra, vob[j], v_alpha);                              \
+                v_alpha = fmaf(ra, q[j], v_alpha);                                                        \
+                bufr[j] = fmaf(q2.x, fac, bufr[j]);                                                       \
+                bufg[j] = fmaf(q2.y, fac, bufg[j]);                                                       \
+                bufb[j] = fmaf(q2.z, fac, bufb[j]);                                                       \
+                /* v_sigma = -opac*vis*v_alpha = -w (backward.cu:323); v_opacity += vis*v_alpha = w/opac */ \
+                const float w = au * v_alpha;                                                             \
+                const float wdy = w * dy;                                                                 \
+                s0 += w;                                                                                  \
+                s1 += wdy;                                                                                \
+                s2 = fmaf(wdy, dy, s2);                                                                   \
+            }                                                                                             \
+        }                                                                                                 \
+        if (jhi == j) break;                                                                              \
+    }
+                switch (jlo) {
+                    case 0: GSB_BWD_SLOT(0)
+                    case 1: GSB_BWD_SLOT(1)
+                    case 2: GSB_BWD_SLOT(2)
+                    case 3: GSB_BWD_SLOT(3)
+                    case 4: GSB_BWD_SLOT(4)
+                    case 5: GSB_BWD_SLOT(5)
+                    case 6: GSB_BWD_SLOT(6)
+                    default: GSB_BWD_SLOT(7)
                 }
+#undef GSB_BWD_SLOT
                 const int k = __float_as_int(q0.w);
                 float *row = grad_rows + (size_t)k * GSB_GRAD_ROW_FLOATS;
                 if (!__any_sync(0xffffffffu, any)) {

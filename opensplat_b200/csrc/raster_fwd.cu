@@ -126,30 +126,44 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 const float dx = q0.x - px;
                 const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
                 const float bdx = q1.y * dx;
-#pragma unroll
-                for (int j = 0; j < RK_PIX; ++j) {
-                    if (!((rm >> j) & 1u)) continue;                         // warp-uniform
-                    const float dy = q0.y - py[j];
-                    // sigma = (a/2)dx^2 + (c/2)dy^2 + b dx dy   (forward.cu:340-342)
-                    const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);
-                    if (__float_as_uint(sigma) <= __float_as_uint(smax)) {    // 0 <= sigma <= smax, no exp
-                        // alpha = min(0.999, opac * exp(-sigma)) = min(0.999, 2^(log2 opac - sigma log2 e))
-                        const float alpha = fminf(0.999f, ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z)));
-                        if (alpha >= (1.f / 255.f)) {
-                            const float next_T = T[j] * (1.f - alpha);
-                            if (next_T <= 1e-4f) {                           // terminate BEFORE blending
-                                if (T[j] > 0.f) { T[j] = -T[j]; done |= 1u << j; }
-                            } else {
-                                const float vis = alpha * T[j];
-                                cr[j] = fmaf(q2.x, vis, cr[j]);
-                                cg[j] = fmaf(q2.y, vis, cg[j]);
-                                cb[j] = fmaf(q2.z, vis, cb[j]);
-                                T[j] = next_T;
-                                last[j] = idx0 + t;
-                            }
-                        }
-                    }
+                // visit only the slots jlo..jhi inside the record's y-extent: computed jump to the first,
+                // one warp-uniform compare per visited slot to leave (no per-slot test for skipped slots)
+                const int jlo = __ffs(rm) - 1, jhi = 31 - __clz(rm);
+#define GSB_FWD_SLOT(j)                                                                                   \
+    {                                                                                                     \
+        const float dy = q0.y - py[j];                                                                    \
+        /* sigma = (a/2)dx^2 + (c/2)dy^2 + b dx dy   (forward.cu:340-342) */                              \
+        const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);                                          \
+        if (__float_as_uint(sigma) <= __float_as_uint(smax)) { /* 0 <= sigma <= smax, no exp */           \
+            /* alpha = min(0.999, opac*exp(-sigma)) = min(0.999, 2^(log2 opac - sigma log2 e)) */         \
+            const float alpha = fminf(0.999f, ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z)));                 \
+            if (alpha >= (1.f / 255.f)) {                                                                 \
+                const float next_T = T[j] * (1.f - alpha);                                                \
+                if (next_T <= 1e-4f) { /* terminate BEFORE blending */                                    \
+                    if (T[j] > 0.f) { T[j] = -T[j]; done |= 1u << j; }                                    \
+                } else {                                                                                  \
+                    const float vis = alpha * T[j];                                                       \
+                    cr[j] = fmaf(q2.x, vis, cr[j]);                                                       \
+                    cg[j] = fmaf(q2.y, vis, cg[j]);                                                       \
+                    cb[j] = fmaf(q2.z, vis, cb[j]);                                                       \
+                    T[j] = next_T;                                                                        \
+                    last[j] = idx0 + t;                                                                   \
+                }                                                                                         \
+            }                                                                                             \
+        }                                                                                                 \
+        if (jhi == j) break;                                                                              \
+    }
+                switch (jlo) {
+                    case 0: GSB_FWD_SLOT(0)
+                    case 1: GSB_FWD_SLOT(1)
+                    case 2: GSB_FWD_SLOT(2)
+                    case 3: GSB_FWD_SLOT(3)
+                    case 4: GSB_FWD_SLOT(4)
+                    case 5: GSB_FWD_SLOT(5)
+                    case 6: GSB_FWD_SLOT(6)
+                    default: GSB_FWD_SLOT(7)
                 }
+#undef GSB_FWD_SLOT
             }
             if (__all_sync(0xffffffffu, done == 0xffu)) { ++c; break; }  // whole tile saturated
             __syncwarp();

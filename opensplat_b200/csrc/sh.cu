@@ -62,7 +62,8 @@ __device__ __forceinline__ int nb_of(int degrees_to_use) {
 template <int K>
 __global__ void __launch_bounds__(SH_THREADS)
 sh_forward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
-                  const float *__restrict__ coeffs, float *__restrict__ colors, int vec_ok) {
+                  const float *__restrict__ coeffs, float *__restrict__ colors, int vec_ok, int fuse_rgb,
+                  float bias) {
     constexpr int C = 3 * K;
     constexpr int S = sh_row_stride(K);
     __shared__ __align__(16) float tile[SH_THREADS * S];
@@ -106,6 +107,11 @@ sh_forward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
             c2 += Y[b] * row[3 * b + 2];
         }
     }
+    if (fuse_rgb) {  // fused glue of model.cpp:192: rgbs = clamp_min(colors + 0.5, 0)
+        c0 = fmaxf(c0 + bias, 0.f);
+        c1 = fmaxf(c1 + bias, 0.f);
+        c2 = fmaxf(c2 + bias, 0.f);
+    }
     colors[3 * g] = c0;
     colors[3 * g + 1] = c1;
     colors[3 * g + 2] = c2;
@@ -114,7 +120,8 @@ sh_forward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
 template <int K>
 __global__ void __launch_bounds__(SH_THREADS)
 sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
-                   const float *__restrict__ v_colors, float *__restrict__ v_coeffs, int vec_ok) {
+                   const float *__restrict__ v_colors, float *__restrict__ v_coeffs, int vec_ok,
+                   const float *__restrict__ rgb_mask) {
     constexpr int C = 3 * K;
     constexpr int S = sh_row_stride(K);
     __shared__ __align__(16) float tile[SH_THREADS * S];
@@ -126,7 +133,12 @@ sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs
         const int g = g0 + t;
         float Y[K];
         sh_basis(nb, viewdirs[3 * g], viewdirs[3 * g + 1], viewdirs[3 * g + 2], Y);
-        const float v0 = v_colors[3 * g], v1 = v_colors[3 * g + 1], v2 = v_colors[3 * g + 2];
+        float v0 = v_colors[3 * g], v1 = v_colors[3 * g + 1], v2 = v_colors[3 * g + 2];
+        if (rgb_mask) {  // gradient of clamp_min(colors + bias, 0): pass where the forward output was > 0
+            v0 = (rgb_mask[3 * g] > 0.f) ? v0 : 0.f;
+            v1 = (rgb_mask[3 * g + 1] > 0.f) ? v1 : 0.f;
+            v2 = (rgb_mask[3 * g + 2] > 0.f) ? v2 : 0.f;
+        }
         float row[S];
 #pragma unroll
         for (int b = 0; b < K; ++b) {
@@ -171,40 +183,68 @@ int bases_of_degree(int degree) {
 
 }  // namespace
 
-extern "C" int gsb_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs,
-                              const float *coeffs, float *colors, gsb_stream_t stream) {
+static int launch_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *coeffs,
+                             float *colors, int fuse_rgb, float bias, gsb_stream_t stream) {
     GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
     if (n == 0) return 0;
     GSB_CHECK_ARG(viewdirs && coeffs && colors);
     cudaStream_t s = (cudaStream_t)stream;
     int grid = gsb_div_up(n, SH_THREADS);
     int vec_ok = ((uintptr_t)coeffs % 16) == 0;
+#define GSB_SH_F(K) sh_forward_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok, fuse_rgb, bias)
     switch (degree) {
-        case 0: sh_forward_kernel<1><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
-        case 1: sh_forward_kernel<4><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
-        case 2: sh_forward_kernel<9><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
-        case 3: sh_forward_kernel<16><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
-        default: sh_forward_kernel<25><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok); break;
+        case 0: GSB_SH_F(1); break;
+        case 1: GSB_SH_F(4); break;
+        case 2: GSB_SH_F(9); break;
+        case 3: GSB_SH_F(16); break;
+        default: GSB_SH_F(25); break;
     }
+#undef GSB_SH_F
     GSB_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int gsb_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs,
-                               const float *v_colors, float *v_coeffs, gsb_stream_t stream) {
+static int launch_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *v_colors,
+                              float *v_coeffs, const float *rgb_mask, gsb_stream_t stream) {
     GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
     if (n == 0) return 0;
     GSB_CHECK_ARG(viewdirs && v_colors && v_coeffs);
     cudaStream_t s = (cudaStream_t)stream;
     int grid = gsb_div_up(n, SH_THREADS);
     int vec_ok = ((uintptr_t)v_coeffs % 16) == 0;
+#define GSB_SH_B(K) sh_backward_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok, rgb_mask)
     switch (degree) {
-        case 0: sh_backward_kernel<1><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
-        case 1: sh_backward_kernel<4><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
-        case 2: sh_backward_kernel<9><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
-        case 3: sh_backward_kernel<16><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
-        default: sh_backward_kernel<25><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok); break;
+        case 0: GSB_SH_B(1); break;
+        case 1: GSB_SH_B(4); break;
+        case 2: GSB_SH_B(9); break;
+        case 3: GSB_SH_B(16); break;
+        default: GSB_SH_B(25); break;
     }
+#undef GSB_SH_B
     GSB_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int gsb_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs,
+                              const float *coeffs, float *colors, gsb_stream_t stream) {
+    return launch_sh_forward(n, degree, degrees_to_use, viewdirs, coeffs, colors, 0, 0.f, stream);
+}
+
+extern "C" int gsb_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs,
+                               const float *v_colors, float *v_coeffs, gsb_stream_t stream) {
+    return launch_sh_backward(n, degree, degrees_to_use, viewdirs, v_colors, v_coeffs, nullptr, stream);
+}
+
+// Fused variants: rgbs = clamp_min(SH(coeffs) + bias, 0) in one pass (model.cpp:188-192)
+// and its VJP: v_coeffs = Y (x) (v_rgbs * [rgbs > 0]).
+extern "C" int gsb_sh_forward_rgb(int n, int degree, int degrees_to_use, const float *viewdirs,
+                                  const float *coeffs, float bias, float *rgbs, gsb_stream_t stream) {
+    return launch_sh_forward(n, degree, degrees_to_use, viewdirs, coeffs, rgbs, 1, bias, stream);
+}
+
+extern "C" int gsb_sh_backward_rgb(int n, int degree, int degrees_to_use, const float *viewdirs,
+                                   const float *rgbs, const float *v_rgbs, float *v_coeffs,
+                                   gsb_stream_t stream) {
+    GSB_CHECK_ARG(n == 0 || rgbs);
+    return launch_sh_backward(n, degree, degrees_to_use, viewdirs, v_rgbs, v_coeffs, rgbs, stream);
 }

@@ -140,9 +140,8 @@ class SplatPipeline:
         fx, fy, cx, cy = self.intr
         p = self.p
         self._stage("sh_fwd")
-        capi.check(L.gsb_sh_forward(n, self.deg, self.deg, P(self.viewdirs), P(p["coeffs"]), P(self.colors), s))
-        # glue of model.cpp:192: rgbs = clamp_min(colors + 0.5, 0)
-        torch.clamp_min(torch.add(self.colors, 0.5, out=self.rgbs), 0.0, out=self.rgbs)
+        # SH colour with the glue of model.cpp:192 fused: rgbs = clamp_min(colors + 0.5, 0)
+        capi.check(L.gsb_sh_forward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(p["coeffs"]), 0.5, P(self.rgbs), s))
         self._stage("project_fwd")
         capi.check(L.gsb_project_forward(n, P(p["means"]), P(p["scales"]), 1.0, P(p["quats"]), P(self.viewmat),
                                          P(self.projmat), fx, fy, cx, cy, H, W, self.tb[0], self.tb[1], 0.01,
@@ -205,7 +204,6 @@ class SplatPipeline:
         p, g = self.p, self.g
         cnt = H * W * 3
         self._stage("loss")
-        self.loss.zero_()
         capi.check(L.gsb_mse_loss_grad(cnt, P(self.out_img), P(self.target), P(self.v_img), P(self.loss), 1.0 / cnt, s))
         self._stage("raster_bwd")
         capi.check(L.gsb_rasterize_backward(H, W, self.tb[0], self.tb[1], n, m, P(self.tile_bins), P(self.conics),
@@ -213,16 +211,15 @@ class SplatPipeline:
                                             P(self.final_Ts), P(self.final_idx),
                                             P(self.v_img), None, P(self.grad_rows), P(self.v_xy), P(self.v_conic),
                                             P(self.v_rgbs), P(g["opacities"]), s))
-        # glue: gradient of clamp_min(colors + 0.5, 0)
-        self._stage("glue_bwd")
-        self.v_rgbs.mul_(self.rgbs > 0)
         self._stage("project_bwd")
         capi.check(L.gsb_project_backward(n, P(p["means"]), P(p["scales"]), 1.0, P(p["quats"]), P(self.viewmat),
                                           P(self.projmat), fx, fy, cx, cy, H, W, None, P(self.radii), P(self.conics),
                                           P(self.v_xy), None, P(self.v_conic), P(g["means"]), P(g["scales"]),
                                           P(g["quats"]), s))
         self._stage("sh_bwd")
-        capi.check(L.gsb_sh_backward(n, self.deg, self.deg, P(self.viewdirs), P(self.v_rgbs), P(g["coeffs"]), s))
+        # SH VJP with the gradient of the clamp fused (mask = forward rgbs > 0)
+        capi.check(L.gsb_sh_backward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(self.rgbs), P(self.v_rgbs),
+                                         P(g["coeffs"]), s))
         self._stage("end_bwd")
         return self.loss
 

@@ -55,6 +55,22 @@ def test_sh_ragged_sizes(n, deg):
     assert np.abs(npy(vc) - orc.sh_backward(deg, K, vd, vcol)).max() <= 3e-6
 
 
+def test_sh_fused_rgb_variants():
+    from opensplat_b200 import capi
+    g = load_golden("sh_deg3")
+    n = g["viewdirs"].shape[0]
+    vd, co, w = cu(g["viewdirs"]), cu(g["coeffs"]).requires_grad_(), cu(g["wgt"])
+    ref = torch.clamp_min(ops.SphericalHarmonics.apply(3, vd, co) + 0.5, 0.0)
+    (ref * w).sum().backward()
+    L = capi.lib()
+    rgbs = torch.empty((n, 3), device=DEV)
+    vco = torch.empty((n, 16, 3), device=DEV)
+    capi.check(L.gsb_sh_forward_rgb(n, 3, 3, capi.ptr(vd), capi.ptr(co.detach()), 0.5, capi.ptr(rgbs), capi.stream()))
+    capi.check(L.gsb_sh_backward_rgb(n, 3, 3, capi.ptr(vd), capi.ptr(rgbs), capi.ptr(w), capi.ptr(vco), capi.stream()))
+    assert torch.equal(rgbs, ref.detach()) and torch.equal(vco, co.grad)
+    assert float((rgbs == 0).float().mean()) > 0.05   # the clamp is active on this data
+
+
 # ------------------------------------------------------------------------------- projection + bins
 def _scene(n, W, H, scale, opacity=(0.05, 0.35), seed=0, **kw):
     return make_scene(n, W, H, scale=scale, sh_degree=0, opacity=opacity, seed=seed, **kw)
