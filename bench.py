@@ -182,10 +182,14 @@ def run_ours(args):
     target_host = torch.from_numpy(rng.uniform(0, 1, (H, W, 3)).astype(np.float32)).pin_memory()
     pipe.target.copy_(target_host, non_blocking=True)
 
+    if world > 1 and args.exchange == "fused":
+        from opensplat_b200.multigpu import ViewParallelExchange
+        pipe.exchange = ViewParallelExchange(pipe, cam["cam_pos"])
+
     def step_fwd_bwd():
         pipe.forward()
-        pipe.backward()
-        if world > 1:
+        pipe.backward()       # with pipe.exchange: fused multi-view SH backward + NVLink exchange inside
+        if world > 1 and pipe.exchange is None:
             dist.all_reduce(pipe.grad_flat, op=dist.ReduceOp.SUM)
         pipe._collect()
 
@@ -308,7 +312,8 @@ def run_ours(args):
         "config": {"workload": args.workload, "gaussians": n, "width": W, "height": H, "sh_degree": 3,
                    "intersections_M": m_timed, "views_per_gpu": 1, "parallelism": f"dp{world}-views",
                    "step": "sh+project+scan/emit/sort/bins+blend fwd, mse, blend+project+sh bwd"
-                           + (", nccl allreduce(flat grads)" if world > 1 else ""),
+                           + ((", fused multi-view SH bwd over NVLink peer loads + nccl allreduce(geometry grads)"
+                               if args.exchange == "fused" else ", nccl allreduce(flat grads)") if world > 1 else ""),
                    "l2_policy": "inputs larger than L2 (>300 MB of parameters/records per step vs 126 MB L2)"},
         "train_iters_per_s": 1e3 / ms_train, "train_ms_per_iter": ms_train,
         "e2e": {"value": e2e_value, "unit": "Mpixel/s", "ms_per_step": ms_e2e,
@@ -339,6 +344,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_1M_1080p_sh3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused multi-view SH backward over peer memory (default) or plain NCCL all-reduce")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

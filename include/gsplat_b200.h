@@ -65,6 +65,18 @@ int gsb_sh_forward_rgb(int n, int degree, int degrees_to_use, const float *viewd
 int gsb_sh_backward_rgb(int n, int degree, int degrees_to_use, const float *viewdirs, const float *rgbs,
                         const float *v_rgbs, float *v_coeffs, gsb_stream_t stream);
 
+/* Data-parallel training: SH VJP fused with the cross-GPU gradient exchange.
+ * gsb_mask_rgb_grad: v_rgbs *= [rgbs > 0] in place (gradient of the clamp, done before exposing v_rgbs).
+ * gsb_sh_backward_multiview: v_coeffs[g] = scale * sum_r Y(normalize(means[g] - cam_positions[r])) (x)
+ *   v_rgbs_per_view[r][g], r < num_views.  v_rgbs_per_view is a DEVICE array of num_views device pointers
+ *   ([n,3] each); entries may be peer-mapped pointers of other GPUs (CUDA IPC / symmetric memory): the
+ *   kernel reads them over NVLink while it computes, replacing "sh_backward + all-reduce of 12K B/Gaussian"
+ *   by an exchange of 12 B/Gaussian/view.  cam_positions is a device [num_views,3] array. */
+int gsb_mask_rgb_grad(int n, const float *rgbs, float *v_rgbs, gsb_stream_t stream);
+int gsb_sh_backward_multiview(int n, int degree, int degrees_to_use, const float *means, int num_views,
+                              const float *cam_positions, const float *const *v_rgbs_per_view, float scale,
+                              float *v_coeffs, gsb_stream_t stream);
+
 /* ---- Projection ------------------------------------------------------------------------------
  * gsb_project_forward replaces project_gaussians_forward_tensor (bindings.h:42-65,
  *   bindings.cu:133-207, kernel forward.cu:19-103).  Outputs cov3d [n,6], xys [n,2], depths [n]

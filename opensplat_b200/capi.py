@@ -21,6 +21,8 @@ _SIGS = {
     "gsb_sh_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "gsb_sh_forward_rgb": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "gsb_sh_backward_rgb": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_mask_rgb_grad": (_i, [_i, _vp, _vp, _vp]),
+    "gsb_sh_backward_multiview": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp]),
     "gsb_project_forward": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _f,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_project_backward": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i,

@@ -170,6 +170,75 @@ sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs
     }
 }
 
+// Multi-view SH VJP fused with the cross-GPU exchange (data-parallel training): instead of
+// all-reducing the [N,K,3] coefficient gradients (192 B/Gaussian at degree 3), every rank exposes only its
+// view's colour gradient v_rgb_r [N,3] (12 B/Gaussian) in peer-mapped memory and THIS kernel forms
+//   v_coeffs[g] = scale * sum_r Y(normalize(mean_g - cam_r)) (x) v_rgb_r[g]
+// reading the peers' v_rgb_r directly over NVLink (P2P loads on mapped pointers) while it computes; the
+// rank-1 structure of the SH VJP makes the local expansion exact.  NVLink traffic per rank drops from
+// 2(G-1)/G x 192 B to (G-1) x 12 B per Gaussian and the separate sh_backward pass disappears.
+template <int K>
+__global__ void __launch_bounds__(SH_THREADS)
+sh_backward_multiview_kernel(int n, int degrees_to_use, const float *__restrict__ means, int num_views,
+                             const float *__restrict__ cam_pos, const float *const *__restrict__ v_rgb_views,
+                             float scale, float *__restrict__ v_coeffs, int vec_ok) {
+    constexpr int C = 3 * K;
+    constexpr int S = sh_row_stride(K);
+    __shared__ __align__(16) float tile[SH_THREADS * S];
+    const int g0 = blockIdx.x * SH_THREADS;
+    const int ng = min(SH_THREADS, n - g0);
+    const int nb = min(nb_of(degrees_to_use), K);
+    const int t = threadIdx.x;
+    if (t < ng) {
+        const int g = g0 + t;
+        const float mx = means[3 * g], my = means[3 * g + 1], mz = means[3 * g + 2];
+        float row[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) row[j] = 0.f;
+        for (int r = 0; r < num_views; ++r) {
+            const float *vr = v_rgb_views[r];  // local or peer-mapped (NVLink) pointer
+            const float v0 = vr[3 * g], v1 = vr[3 * g + 1], v2 = vr[3 * g + 2];
+            if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;  // Gaussian not visible in view r
+            float Y[K];
+            sh_basis(nb, mx - __ldg(cam_pos + 3 * r), my - __ldg(cam_pos + 3 * r + 1),
+                     mz - __ldg(cam_pos + 3 * r + 2), Y);
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                if (b < nb) {
+                    row[3 * b] = fmaf(Y[b], v0, row[3 * b]);
+                    row[3 * b + 1] = fmaf(Y[b], v1, row[3 * b + 1]);
+                    row[3 * b + 2] = fmaf(Y[b], v2, row[3 * b + 2]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < S; j += 4)
+            *reinterpret_cast<float4 *>(&tile[t * S + j]) =
+                make_float4(scale * row[j], scale * row[j + 1], scale * row[j + 2], scale * row[j + 3]);
+    }
+    __syncthreads();
+    float *dst = v_coeffs + (size_t)g0 * C;
+    const int total = ng * C;
+    if (vec_ok && (C % 4 == 0)) {
+        float4 *dst4 = reinterpret_cast<float4 *>(dst);
+        for (int f = threadIdx.x; f < total / 4; f += SH_THREADS) {
+            int e = 4 * f, g = e / C, j = e - g * C;
+            stg_stream4(dst4 + f, *reinterpret_cast<const float4 *>(&tile[g * S + j]));
+        }
+    } else {
+        for (int e = threadIdx.x; e < total; e += SH_THREADS) {
+            int g = e / C, j = e - g * C;
+            dst[e] = tile[g * S + j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mask_rgb_grad_kernel(long long n3, const float *__restrict__ rgbs, float *__restrict__ v_rgbs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3 && !(rgbs[i] > 0.f)) v_rgbs[i] = 0.f;
+}
+
 int bases_of_degree(int degree) {
     switch (degree) {
         case 0: return 1;
@@ -247,4 +316,40 @@ extern "C" int gsb_sh_backward_rgb(int n, int degree, int degrees_to_use, const 
                                    gsb_stream_t stream) {
     GSB_CHECK_ARG(n == 0 || rgbs);
     return launch_sh_backward(n, degree, degrees_to_use, viewdirs, v_rgbs, v_coeffs, rgbs, stream);
+}
+
+// In-place gradient of clamp_min(. , 0): v_rgbs *= [rgbs > 0]  (what gsb_sh_backward_rgb does internally;
+// needed separately when the SH VJP runs in the fused multi-view kernel).
+extern "C" int gsb_mask_rgb_grad(int n, const float *rgbs, float *v_rgbs, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(rgbs && v_rgbs);
+    const long long n3 = 3ll * n;
+    mask_rgb_grad_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n3, rgbs, v_rgbs);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gsb_sh_backward_multiview(int n, int degree, int degrees_to_use, const float *means,
+                                         int num_views, const float *cam_positions,
+                                         const float *const *v_rgbs_per_view, float scale, float *v_coeffs,
+                                         gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
+    GSB_CHECK_ARG(num_views >= 1);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(means && cam_positions && v_rgbs_per_view && v_coeffs);
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = gsb_div_up(n, SH_THREADS);
+    int vec_ok = ((uintptr_t)v_coeffs % 16) == 0;
+#define GSB_SH_M(K) sh_backward_multiview_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, means, num_views, cam_positions, v_rgbs_per_view, scale, v_coeffs, vec_ok)
+    switch (degree) {
+        case 0: GSB_SH_M(1); break;
+        case 1: GSB_SH_M(4); break;
+        case 2: GSB_SH_M(9); break;
+        case 3: GSB_SH_M(16); break;
+        default: GSB_SH_M(25); break;
+    }
+#undef GSB_SH_M
+    GSB_LAUNCH_CHECK();
+    return 0;
 }

@@ -80,6 +80,7 @@ class SplatPipeline:
         self.m = 0
         if m_capacity:
             self._grow(int(m_capacity))
+        self.exchange = None  # multigpu.ViewParallelExchange (fused SH backward + NVLink exchange)
         self.stage_timing = stage_timing
         self.stage_ms = {}
         self._ev = []
@@ -205,21 +206,26 @@ class SplatPipeline:
         cnt = H * W * 3
         self._stage("loss")
         capi.check(L.gsb_mse_loss_grad(cnt, P(self.out_img), P(self.target), P(self.v_img), P(self.loss), 1.0 / cnt, s))
+        v_rgbs = self.exchange.v_rgbs_buffer() if self.exchange is not None else self.v_rgbs
         self._stage("raster_bwd")
         capi.check(L.gsb_rasterize_backward(H, W, self.tb[0], self.tb[1], n, m, P(self.tile_bins), P(self.conics),
                                             P(p["opacities"]), P(self.records), P(self.cum), P(self.background),
                                             P(self.final_Ts), P(self.final_idx),
                                             P(self.v_img), None, P(self.grad_rows), P(self.v_xy), P(self.v_conic),
-                                            P(self.v_rgbs), P(g["opacities"]), s))
+                                            P(v_rgbs), P(g["opacities"]), s))
         self._stage("project_bwd")
         capi.check(L.gsb_project_backward(n, P(p["means"]), P(p["scales"]), 1.0, P(p["quats"]), P(self.viewmat),
                                           P(self.projmat), fx, fy, cx, cy, H, W, None, P(self.radii), P(self.conics),
                                           P(self.v_xy), None, P(self.v_conic), P(g["means"]), P(g["scales"]),
                                           P(g["quats"]), s))
         self._stage("sh_bwd")
-        # SH VJP with the gradient of the clamp fused (mask = forward rgbs > 0)
-        capi.check(L.gsb_sh_backward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(self.rgbs), P(self.v_rgbs),
-                                         P(g["coeffs"]), s))
+        if self.exchange is not None:
+            # data-parallel: SH VJP fused with the cross-GPU exchange (also all-reduces the geometry grads)
+            self.exchange.exchange(average=True)
+        else:
+            # SH VJP with the gradient of the clamp fused (mask = forward rgbs > 0)
+            capi.check(L.gsb_sh_backward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(self.rgbs), P(self.v_rgbs),
+                                             P(g["coeffs"]), s))
         self._stage("end_bwd")
         return self.loss
 
@@ -243,7 +249,7 @@ class SplatPipeline:
         """fwd + bwd (+ one NCCL all-reduce of the flat per-Gaussian gradient buffer) + fused Adam."""
         self.forward()
         loss = self.backward()
-        if world_size > 1:
+        if world_size > 1 and self.exchange is None:
             import torch.distributed as dist
             dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM)
             self.grad_flat.mul_(1.0 / world_size)
