@@ -242,10 +242,31 @@ def run_ours(args):
     use_cpp = cpp_ops.available()
     cops = cpp_ops.ops() if use_cpp else None
 
+    # H2D of every step's inputs (target image + camera) from pinned memory runs on a copy stream, one step
+    # ahead of the compute (double buffer), so PCIe overlaps the kernels; it is still inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [dict(tgt=torch.empty_like(pipe.target), vm=torch.empty_like(pipe.viewmat),
+                  pm=torch.empty_like(pipe.projmat), ev=torch.cuda.Event(), used=torch.cuda.Event()) for _ in range(2)]
+    state = {"i": 0}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot["used"])      # the compute that last read this slot has finished
+            slot["tgt"].copy_(target_host, non_blocking=True)
+            slot["vm"].copy_(view_host, non_blocking=True)
+            slot["pm"].copy_(proj_host, non_blocking=True)
+            slot["ev"].record(copy_stream)
+
+    for sl in slots:
+        sl["used"].record(torch.cuda.current_stream())
+    prefetch(slots[0])
+
     def step_e2e():
-        tgt = target_host.to(dev, non_blocking=True)             # H2D: this step's target image
-        vm = view_host.to(dev, non_blocking=True)                # H2D: this step's camera
-        pm = proj_host.to(dev, non_blocking=True)
+        cur = slots[state["i"] % 2]
+        prefetch(slots[(state["i"] + 1) % 2])                    # next step's inputs, overlapped
+        state["i"] += 1
+        torch.cuda.current_stream().wait_event(cur["ev"])       # this step's H2D has landed
+        tgt, vm, pm = cur["tgt"], cur["vm"], cur["pm"]
         for t in P.values():
             t.grad = None
         if use_cpp:   # the libtorch autograd operators a C++ caller of the reference API uses
@@ -263,6 +284,7 @@ def run_ours(args):
         if world > 1:
             for t in P.values():
                 dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
+        cur["used"].record(torch.cuda.current_stream())
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # D2H: the step's result
         torch.cuda.current_stream().synchronize()
 

@@ -71,15 +71,17 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         const float px = (float)X;
         const float tile_x0 = (float)(tx * GSB_TILE), tile_y0 = (float)(ty * GSB_TILE);
 
-        float T[RK_PIX], bufr[RK_PIX], bufg[RK_PIX], bufb[RK_PIX], py[RK_PIX];
-        float vor[RK_PIX], vog[RK_PIX], vob[RK_PIX], q[RK_PIX];
+        // Per pixel only the SCALAR Bq = (colour behind) . v_out - q is tracked instead of the reference's 3-vector
+        // `buffer` (backward.cu:200,319-321): v_alpha = sum_c (rgb_c T - buffer_c ra) v_out_c + ra q
+        //                                            = T (rgb . v_out) - ra (buffer . v_out - q).
+        float T[RK_PIX], Bq[RK_PIX], py[RK_PIX];
+        float vor[RK_PIX], vog[RK_PIX], vob[RK_PIX];
         int binf[RK_PIX];
         int my_max = -1;
 #pragma unroll
         for (int j = 0; j < RK_PIX; ++j) {
             const int Y = Y0 + 2 * j;
             py[j] = (float)Y;
-            bufr[j] = bufg[j] = bufb[j] = 0.f;
             if (X < img_w && Y < img_h) {
                 const size_t p = (size_t)Y * img_w + X;
                 const float Tf = final_Ts[p];
@@ -87,10 +89,10 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 vor[j] = v_output[3 * p]; vog[j] = v_output[3 * p + 1]; vob[j] = v_output[3 * p + 2];
                 const float voa = v_output_alpha ? v_output_alpha[p] : 0.f;
                 // backward.cu:313-317: T_final*ra*v_out_alpha - T_final*ra*(bg . v_out)  ==  ra * q
-                q[j] = Tf * (voa - (bg0 * vor[j] + bg1 * vog[j] + bg2 * vob[j]));
+                Bq[j] = -(Tf * (voa - (bg0 * vor[j] + bg1 * vog[j] + bg2 * vob[j])));
                 binf[j] = final_idx[p];
             } else {
-                T[j] = 1.f; vor[j] = vog[j] = vob[j] = 0.f; q[j] = 0.f;
+                T[j] = 1.f; vor[j] = vog[j] = vob[j] = 0.f; Bq[j] = 0.f;
                 binf[j] = -1;  // never valid
             }
             my_max = max(my_max, binf[j]);
@@ -165,13 +167,9 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 a_r = fmaf(fac, vor[j], a_r);                                                             \
                 a_g = fmaf(fac, vog[j], a_g);                                                             \
                 a_b = fmaf(fac, vob[j], a_b);                                                             \
-                float v_alpha = (q2.x * T[j] - bufr[j] * ra) * vor[j];                                    \
-                v_alpha = fmaf(q2.y * T[j] - bufg[j] * ra, vog[j], v_alpha);                              \
-                v_alpha = fmaf(q2.z * T[j] - bufb[j] * ra, vob[j], v_alpha);                              \
-                v_alpha = fmaf(ra, q[j], v_alpha);                                                        \
-                bufr[j] = fmaf(q2.x, fac, bufr[j]);                                                       \
-                bufg[j] = fmaf(q2.y, fac, bufg[j]);                                                       \
-                bufb[j] = fmaf(q2.z, fac, bufb[j]);                                                       \
+                const float d = fmaf(q2.z, vob[j], fmaf(q2.y, vog[j], q2.x * vor[j])); /* rgb . v_out */  \
+                const float v_alpha = fmaf(d, T[j], -(ra * Bq[j]));                                       \
+                Bq[j] = fmaf(d, fac, Bq[j]);                                                              \
                 /* v_sigma = -opac*vis*v_alpha = -w (backward.cu:323); v_opacity += vis*v_alpha = w/opac */ \
                 const float w = au * v_alpha;                                                             \
                 const float wdy = w * dy;                                                                 \
