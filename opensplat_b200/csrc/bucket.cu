@@ -114,6 +114,45 @@ bucket_emit_kernel(int n, const float2 *__restrict__ xys, const float *__restric
         }
 }
 
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
+    unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, m);
+    hi = __shfl_xor_sync(0xffffffffu, hi, m);
+    return ((u64)hi << 32) | lo;
+}
+
+// compare-exchange across lanes at stride j (< 32): the lane keeps the min iff keep_min
+__device__ __forceinline__ u64 cex_shfl(u64 v, int j, bool keep_min) {
+    const u64 o = shfl_xor_u64(v, j);
+    return ((v < o) == keep_min) ? v : o;
+}
+
+// Bitonic network restricted to one 64-element block held as (a = element base+lane, b = element
+// base+32+lane): runs the sub-stages j = 32..1 of merge size k (direction of element i: ascending iff
+// (i & k) == 0), entirely in registers / warp shuffles.
+__device__ __forceinline__ void block64_substages(u64 &a, u64 &b, int base, int lane, int k, int jstart) {
+    const int ia = base + lane, ib = ia + 32;
+    const bool asc_a = (ia & k) == 0, asc_b = (ib & k) == 0;
+    if (jstart >= 32) {  // partner of a is b (same thread); both share the direction (k >= 64)
+        const bool sw = (a > b) == asc_a;
+        const u64 t = sw ? b : a;
+        b = sw ? a : b;
+        a = t;
+    }
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        if (j > jstart) continue;
+        const bool lower = (lane & j) == 0;
+        a = cex_shfl(a, j, lower == asc_a);
+        b = cex_shfl(b, j, lower == asc_b);
+    }
+}
+
+// One CTA per tile: sort the tile's composites (depth bits << 32 | k) ascending and write its records.
+// Bitonic sort, 64-bit keys: merges up to 64 elements wide run in registers with warp shuffles (no barrier),
+// only the strides >= 64 of larger merges go through shared memory.
 __global__ void __launch_bounds__(256)
 tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
                       const int *__restrict__ gaussian_ids, const float2 *__restrict__ xys,
@@ -125,23 +164,44 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
     const int2 range = tile_bins[tile];
     const int L = range.y - range.x;
     if (L <= 0) return;
-    int n2 = 1;
+    int n2 = 64;
     while (n2 < L) n2 <<= 1;
     if (n2 > cap) return;  // host guarantees max length <= cap (otherwise it takes the generic path)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nblk = n2 >> 6;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) skey[i] = (i < L) ? comp[range.x + i] : ~0ull;
     __syncthreads();
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-                // t-th compare-exchange of this stage: partner indices (lo, lo + j)
-                const int lo = ((t / j) * (j << 1)) + (t % j);
-                const int hiI = lo + j;
-                const bool asc = ((lo & k) == 0);
-                const unsigned long long a = skey[lo], b = skey[hiI];
-                if ((a > b) == asc) {
-                    skey[lo] = b;
-                    skey[hiI] = a;
+    if (L > 1) {
+        // phase A: every 64-block fully sorted (merge sizes 2..64), alternating directions for later merges
+        for (int blk = warp; blk < nblk; blk += nwarps) {
+            const int base = blk << 6;
+            u64 a = skey[base + lane], b = skey[base + 32 + lane];
+#pragma unroll
+            for (int k = 2; k <= 64; k <<= 1) block64_substages(a, b, base, lane, k, k >> 1);
+            skey[base + lane] = a;
+            skey[base + 32 + lane] = b;
+        }
+        __syncthreads();
+        for (int k = 128; k <= n2; k <<= 1) {
+            for (int j = k >> 1; j >= 64; j >>= 1) {  // wide strides through shared memory
+                for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int hiI = lo + j;
+                    const bool asc = ((lo & k) == 0);
+                    const u64 x = skey[lo], y = skey[hiI];
+                    if ((x > y) == asc) {
+                        skey[lo] = y;
+                        skey[hiI] = x;
+                    }
                 }
+                __syncthreads();
+            }
+            for (int blk = warp; blk < nblk; blk += nwarps) {  // strides 32..1 in registers
+                const int base = blk << 6;
+                u64 a = skey[base + lane], b = skey[base + 32 + lane];
+                block64_substages(a, b, base, lane, k, 32);
+                skey[base + lane] = a;
+                skey[base + 32 + lane] = b;
             }
             __syncthreads();
         }
@@ -219,7 +279,7 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
         gsb_set_error(GSB_ERR_WORKSPACE, "bucket workspace too small", __FILE__, __LINE__);
         return GSB_ERR_WORKSPACE;
     }
-    int cap = 32;
+    int cap = 64;
     while (cap < max_tile_len) cap <<= 1;
     if (cap > BUCKET_MAX_CAP) {
         gsb_set_error(GSB_ERR_UNSUPPORTED, "tile list longer than the in-shared-memory sort capacity; "
