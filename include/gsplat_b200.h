@@ -133,14 +133,15 @@ int gsb_gather_bin_edges(int m, int num_tiles, const int64_t *isect_ids_sorted,
  * unsorted slot) as gsb_map_gaussian_to_intersects + gsb_sort_intersects + gsb_gather_bin_edges +
  * the record packing of gsb_rasterize_forward, without a global sort (what RasterizeGaussians::forward
  * needs between rasterize_gaussians.cpp:62 and :79).
- * gsb_bucket_tile_ranges (before the M read-back): tile_bins [tiles,2], tile_cursor [tiles] (scratch that
- *   phase 2 consumes) and stats[2] = {M, longest tile list} (device int32; read both back in the operator's
+ * gsb_bucket_tile_ranges (before the M read-back): tile_bins [tiles,2], tile_cursor (scratch of
+ *   gsb_bucket_cursor_bytes(tiles) bytes that phase 2 consumes) and stats[2] = {M, longest tile list} (device int32; read both back in the operator's
  *   single D2H copy).
  * gsb_bucket_sort_pack (after it): fills `records` (gsb_raster_records_bytes(m)); optional outputs
  *   sorted_index [m] / gaussian_ids_sorted [m] (NULL to skip).  Returns GSB_ERR_UNSUPPORTED if
  *   max_tile_len > gsb_bucket_max_tile_len() -- take the generic path then.
  * gsb_rasterize_forward_packed: the blend kernel alone on an already packed record stream. */
 int gsb_bucket_max_tile_len(void);
+size_t gsb_bucket_cursor_bytes(int num_tiles);
 size_t gsb_bucket_workspace_bytes(int m);
 int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
                            int32_t *tile_bins, int32_t *tile_cursor, int32_t *stats, gsb_stream_t stream);

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgsplat_b200.so")
+# GSB_LIB overrides the library path (tools/bench_blend.py uses it to A/B kernel variants)
+LIB_PATH = os.environ.get("GSB_LIB") or os.path.join(_HERE, "lib", "libgsplat_b200.so")
 _lib = None
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -40,6 +41,7 @@ _SIGS = {
     "gsb_rasterize_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_bucket_max_tile_len": (_i, []),
+    "gsb_bucket_cursor_bytes": (_sz, [_i]),
     "gsb_bucket_workspace_bytes": (_sz, [_i]),
     "gsb_bucket_tile_ranges": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "gsb_bucket_sort_pack": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,

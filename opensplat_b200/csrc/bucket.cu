@@ -18,6 +18,10 @@
 
 namespace {
 
+// Tile counters / write cursors are padded to one 128-B line each: the ~400 atomics a tile receives then
+// serialise in their own L2 line (and the lines spread over all L2 slices) instead of 32 tiles sharing one.
+constexpr int CUR_STRIDE = 32;  // ints
+
 __device__ __forceinline__ void tile_bbox_of(float2 c, int r, int tiles_x, int tiles_y, int &x0, int &x1, int &y0,
                                              int &y1) {
     // get_tile_bbox (helpers.cuh:17-49) -- same arithmetic as project.cu / binning.cu
@@ -38,7 +42,7 @@ tile_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__
     int x0, x1, y0, y1;
     tile_bbox_of(xys[i], r, tiles_x, tiles_y, x0, x1, y0, y1);
     for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) atomicAdd(&tile_count[ty * tiles_x + tx], 1);
+        for (int tx = x0; tx < x1; ++tx) atomicAdd(&tile_count[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
 }
 
 // single CTA: exclusive scan of tile_count -> tile_bins; zeroes the cursors; max tile length
@@ -53,7 +57,7 @@ tile_scan_kernel(int T, int *__restrict__ tile_count_then_cursor, int2 *__restri
     int carry = 0, my_max = 0;
     for (int base = 0; base < T; base += 1024) {
         const int i = base + threadIdx.x;
-        const int v = (i < T) ? tile_count_then_cursor[i] : 0;
+        const int v = (i < T) ? tile_count_then_cursor[(size_t)i * CUR_STRIDE] : 0;
         my_max = max(my_max, v);
         int inc = v;
 #pragma unroll
@@ -79,7 +83,7 @@ tile_scan_kernel(int T, int *__restrict__ tile_count_then_cursor, int2 *__restri
         if (i < T) {
             // empty tiles keep (0,0) like the reference's zero-initialised tile_bins
             tile_bins[i] = (v > 0) ? make_int2(excl, excl + v) : make_int2(0, 0);
-            tile_count_then_cursor[i] = excl;   // becomes the write cursor of K3
+            tile_count_then_cursor[(size_t)i * CUR_STRIDE] = excl;   // becomes the write cursor of K3
         }
         carry += sm[32];
         __syncthreads();
@@ -107,7 +111,7 @@ bucket_emit_kernel(int n, const float2 *__restrict__ xys, const float *__restric
     const unsigned long long hi = ((unsigned long long)(unsigned)__float_as_int(depths[i])) << 32;
     for (int ty = y0; ty < y1; ++ty)
         for (int tx = x0; tx < x1; ++tx) {
-            const int pos = atomicAdd(&cursor[ty * tiles_x + tx], 1);
+            const int pos = atomicAdd(&cursor[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
             comp[pos] = hi | (unsigned)k;
             gaussian_ids[k] = i;
             ++k;
@@ -239,9 +243,14 @@ constexpr int BUCKET_MAX_CAP = 16384;  // 128 KB of shared memory per CTA
 
 extern "C" int gsb_bucket_max_tile_len(void) { return BUCKET_MAX_CAP; }
 
+extern "C" size_t gsb_bucket_cursor_bytes(int num_tiles) {
+    return (size_t)(num_tiles > 0 ? num_tiles : 1) * CUR_STRIDE * sizeof(int);
+}
+
 extern "C" size_t gsb_bucket_workspace_bytes(int m) { return bucket_layout(m > 0 ? m : 0).total + 256; }
 
-// Phase 1 (before the M read-back): tile sizes -> tile_bins, tile_cursor [tiles] (write cursors for phase 2),
+// Phase 1 (before the M read-back): tile sizes -> tile_bins, tile_cursor (gsb_bucket_cursor_bytes(tiles); the
+// padded write cursors for phase 2),
 // stats = {M, max tile length} (device int32[2]).
 extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
                                       int32_t *tile_bins, int32_t *tile_cursor, int32_t *stats,
@@ -249,7 +258,7 @@ extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *ra
     GSB_CHECK_ARG(n >= 0 && tiles_x > 0 && tiles_y > 0 && tile_bins && tile_cursor && stats);
     const int T = tiles_x * tiles_y;
     cudaStream_t s = (cudaStream_t)stream;
-    GSB_CUDA(cudaMemsetAsync(tile_cursor, 0, (size_t)T * 4, s));
+    GSB_CUDA(cudaMemsetAsync(tile_cursor, 0, gsb_bucket_cursor_bytes(T), s));
     if (n > 0) {
         GSB_CHECK_ARG(xys && radii && ((uintptr_t)xys % 8) == 0);
         tile_count_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, reinterpret_cast<const float2 *>(xys), radii,

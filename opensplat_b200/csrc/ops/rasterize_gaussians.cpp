@@ -73,7 +73,7 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
     const int numTiles = tilesX * tilesY;
     torch::Tensor tileBins = torch::empty({numTiles, 2}, gsb::like(x, torch::kInt32));
     torch::Tensor stats = torch::zeros({2}, gsb::like(x, torch::kInt32));
-    torch::Tensor tileCursor = torch::empty({numTiles}, gsb::like(x, torch::kInt32));
+    torch::Tensor tileCursor = torch::empty({(int64_t)gsb_bucket_cursor_bytes(numTiles) / 4}, gsb::like(x, torch::kInt32));
     if (n > 0) {
         const size_t sb = gsb_cumsum_workspace_bytes(n);
         torch::Tensor sws = torch::empty({(int64_t)sb}, gsb::like(x, torch::kUInt8));

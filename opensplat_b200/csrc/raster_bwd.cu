@@ -22,6 +22,10 @@
 // scheduling and two-level culling as the forward pass.
 #include "raster_common.cuh"
 
+#ifndef GSB_BWD_SLOT_SWITCH
+#define GSB_BWD_SLOT_SWITCH 1
+#endif
+
 int gsb_blend_grid(const void *kernel, int num_tiles);
 
 namespace {
@@ -180,6 +184,7 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         }                                                                                                 \
         if (jhi == j) break;                                                                              \
     }
+#if GSB_BWD_SLOT_SWITCH
                 switch (jlo) {
                     case 0: GSB_BWD_SLOT(0)
                     case 1: GSB_BWD_SLOT(1)
@@ -190,6 +195,19 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                     case 6: GSB_BWD_SLOT(6)
                     default: GSB_BWD_SLOT(7)
                 }
+#else
+                (void)jlo;
+                do {
+                    if (rm & 1u) GSB_BWD_SLOT(0)
+                    if (rm & 2u) GSB_BWD_SLOT(1)
+                    if (rm & 4u) GSB_BWD_SLOT(2)
+                    if (rm & 8u) GSB_BWD_SLOT(3)
+                    if (rm & 16u) GSB_BWD_SLOT(4)
+                    if (rm & 32u) GSB_BWD_SLOT(5)
+                    if (rm & 64u) GSB_BWD_SLOT(6)
+                    if (rm & 128u) GSB_BWD_SLOT(7)
+                } while (0);
+#endif
 #undef GSB_BWD_SLOT
                 const int k = __float_as_int(q0.w);
                 float *row = grad_rows + (size_t)k * GSB_GRAD_ROW_FLOATS;

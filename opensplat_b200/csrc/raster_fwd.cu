@@ -23,6 +23,10 @@
 //    pairs of a typical 1080p scene never reach the exact alpha test.
 #include "raster_common.cuh"
 
+#ifndef GSB_FWD_SLOT_SWITCH
+#define GSB_FWD_SLOT_SWITCH 0
+#endif
+
 namespace {
 
 __global__ void __launch_bounds__(256)
@@ -153,6 +157,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         }                                                                                                 \
         if (jhi == j) break;                                                                              \
     }
+#if GSB_FWD_SLOT_SWITCH
                 switch (jlo) {
                     case 0: GSB_FWD_SLOT(0)
                     case 1: GSB_FWD_SLOT(1)
@@ -163,6 +168,19 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                     case 6: GSB_FWD_SLOT(6)
                     default: GSB_FWD_SLOT(7)
                 }
+#else
+                (void)jlo;
+                do {   // straight-line: one warp-uniform test per slot
+                    if (rm & 1u) GSB_FWD_SLOT(0)
+                    if (rm & 2u) GSB_FWD_SLOT(1)
+                    if (rm & 4u) GSB_FWD_SLOT(2)
+                    if (rm & 8u) GSB_FWD_SLOT(3)
+                    if (rm & 16u) GSB_FWD_SLOT(4)
+                    if (rm & 32u) GSB_FWD_SLOT(5)
+                    if (rm & 64u) GSB_FWD_SLOT(6)
+                    if (rm & 128u) GSB_FWD_SLOT(7)
+                } while (0);
+#endif
 #undef GSB_FWD_SLOT
             }
             if (__all_sync(0xffffffffu, done == 0xffu)) { ++c; break; }  // whole tile saturated

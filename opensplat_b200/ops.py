@@ -187,7 +187,7 @@ def bucket_tile_ranges(xys, radii, tile_bounds_):
     n = xys.shape[0]
     T = tile_bounds_[0] * tile_bounds_[1]
     bins = _empty((T, 2), torch.int32, xys)
-    cursor = _empty((T,), torch.int32, xys)
+    cursor = torch.empty(capi.lib().gsb_bucket_cursor_bytes(T), dtype=torch.uint8, device=xys.device)
     stats = _empty((2,), torch.int32, xys)
     capi.check(capi.lib().gsb_bucket_tile_ranges(n, capi.ptr(capi.f32(xys)), capi.ptr(radii.contiguous()),
                                                  tile_bounds_[0], tile_bounds_[1], capi.ptr(bins), capi.ptr(cursor),

@@ -70,7 +70,7 @@ class SplatPipeline:
         self.background = torch.zeros(3, dtype=f32, device=d)
         self.loss = torch.zeros(1, dtype=f32, device=d)
         self.tile_bins = torch.empty((self.T, 2), dtype=i32, device=d)
-        self.tile_cursor = torch.empty((self.T,), dtype=i32, device=d)
+        self.tile_cursor = torch.empty(self.L.gsb_bucket_cursor_bytes(self.T), dtype=torch.uint8, device=d)
         # ---- camera ----
         self.viewmat = torch.eye(4, dtype=f32, device=d)
         self.projmat = torch.eye(4, dtype=f32, device=d)
