@@ -23,8 +23,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (n, W, H, scale, opacity range)
     "c2_1M_1080p_sh3": (1_000_000, 1920, 1080, 0.02, (0.05, 0.95)),
-    "c3_3M_4k_sh3": (3_000_000, 3840, 2160, 0.02, (0.05, 0.95)),
-    "c5_5M_1440p_dense": (5_000_000, 2560, 1440, 0.04, (0.05, 0.95)),
+    "c3_3M_4k_sh3": (3_000_000, 3840, 2160, 0.01, (0.05, 0.95)),        # same pixel footprints as c2 (focal doubles)
+    "c5_5M_1440p_dense": (5_000_000, 2560, 1440, 0.023, (0.05, 0.95)),   # ~200 blended-candidate splats / pixel
     "c1_1k_256": (1_000, 256, 256, 0.5, (0.05, 0.95)),
 }
 # kernels of OURS launched per fwd+bwd step (counted from the C-ABI implementations):

@@ -154,9 +154,84 @@ __device__ __forceinline__ void block64_substages(u64 &a, u64 &b, int base, int 
     }
 }
 
+// ---- CTA-wide LSD radix sort of a tile's composites, keyed on the 32 depth bits (bits 32..63) --------------
+// Lists longer than 64 use this instead of a bitonic network (cost linear in L instead of L log^2 L; dense
+// scenes have thousands of records per tile).  4 stable 8-bit passes; the items stay in registers between the
+// rank and scatter steps, so ONE shared buffer suffices.  Depth ties (rare) come out in arrival order, which
+// the bucket emission makes arbitrary: a final fix-up re-sorts every run of equal depths by k, restoring the
+// reference's stable order (tile, depth, ascending unsorted slot).
+template <int ITEMS>
+__device__ __forceinline__ void cta_radix_sort_depth(u64 *buf, unsigned (*whist)[256], unsigned *bin_base,
+                                                    unsigned *s_flag) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wbase = w * 32 * ITEMS;  // warp w owns the contiguous range [wbase, wbase + 32*ITEMS)
+    u64 key[ITEMS];
+    unsigned rank[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) key[r] = buf[wbase + r * 32 + lane];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 32 + 8 * pass;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) whist[k][threadIdx.x] = 0;
+        if (threadIdx.x == 0) *s_flag = 0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const unsigned d = (unsigned)(key[r] >> shift) & 0xffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            unsigned prev = 0;
+            if (lane == leader) {
+                prev = whist[w][d];
+                whist[w][d] = prev + __popc(peers);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, leader);
+            rank[r] = prev + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // thread d owns digit d: offsets across warps, then exclusive scan over the 256 digits
+            const unsigned d = threadIdx.x;
+            unsigned run = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned c = whist[k][d];
+                whist[k][d] = run;
+                run += c;
+            }
+            if (run == 256u * ITEMS) *s_flag = 1;  // every key has this digit: pass is a no-op
+            unsigned inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) bin_base[256 + w] = inc;   // warp totals
+            __syncthreads();
+            unsigned woff = 0;
+            for (int k = 0; k < w; ++k) woff += bin_base[256 + k];
+            bin_base[d] = woff + inc - run;
+        }
+        __syncthreads();
+        if (*s_flag == 0) {
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                const unsigned d = (unsigned)(key[r] >> shift) & 0xffu;
+                buf[bin_base[d] + whist[w][d] + rank[r]] = key[r];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) key[r] = buf[wbase + r * 32 + lane];
+        }
+        __syncthreads();
+    }
+}
+
 // One CTA per tile: sort the tile's composites (depth bits << 32 | k) ascending and write its records.
-// Bitonic sort, 64-bit keys: merges up to 64 elements wide run in registers with warp shuffles (no barrier),
-// only the strides >= 64 of larger merges go through shared memory.
+//  * L <= 64: one warp, bitonic network in registers / shuffles;
+//  * longer:  CTA-wide LSD radix sort on the depth bits + tie fix-up (cta_radix_sort_depth).
+template <int MAXI>   // largest items-per-thread instantiation compiled in (register budget): 4, 16 or 64
 __global__ void __launch_bounds__(256)
 tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
                       const int *__restrict__ gaussian_ids, const float2 *__restrict__ xys,
@@ -164,51 +239,53 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
                       const float *__restrict__ opacities, GsbRecord *__restrict__ records,
                       int *__restrict__ sorted_index, int *__restrict__ gaussian_ids_sorted) {
     extern __shared__ unsigned long long skey[];
+    __shared__ unsigned whist[8][256];
+    __shared__ unsigned bin_base[256 + 8];
+    __shared__ unsigned s_flag;
     const int tile = blockIdx.x;
     const int2 range = tile_bins[tile];
     const int L = range.y - range.x;
     if (L <= 0) return;
-    int n2 = 64;
+    int n2 = 64;               // padded length: 64 (bitonic) or a multiple of 256 (radix), power of two
     while (n2 < L) n2 <<= 1;
-    if (n2 > cap) return;  // host guarantees max length <= cap (otherwise it takes the generic path)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int nblk = n2 >> 6;
+    if (n2 > 64 && n2 < 256) n2 = 256;
+    if (n2 > cap) return;      // host guarantees max length <= cap (otherwise it takes the generic path)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) skey[i] = (i < L) ? comp[range.x + i] : ~0ull;
     __syncthreads();
     if (L > 1) {
-        // phase A: every 64-block fully sorted (merge sizes 2..64), alternating directions for later merges
-        for (int blk = warp; blk < nblk; blk += nwarps) {
-            const int base = blk << 6;
-            u64 a = skey[base + lane], b = skey[base + 32 + lane];
+        if (n2 == 64) {
+            if (warp == 0) {
+                u64 a = skey[lane], b = skey[32 + lane];
 #pragma unroll
-            for (int k = 2; k <= 64; k <<= 1) block64_substages(a, b, base, lane, k, k >> 1);
-            skey[base + lane] = a;
-            skey[base + 32 + lane] = b;
+                for (int k = 2; k <= 64; k <<= 1) block64_substages(a, b, 0, lane, k, k >> 1);
+                skey[lane] = a;
+                skey[32 + lane] = b;
+            }
+        } else {
+            const int items = n2 >> 8;
+            if (items == 1) cta_radix_sort_depth<1>(skey, whist, bin_base, &s_flag);
+            else if (items == 2) cta_radix_sort_depth<2>(skey, whist, bin_base, &s_flag);
+            else if (items == 4) cta_radix_sort_depth<4>(skey, whist, bin_base, &s_flag);
+            else if (MAXI >= 16 && items == 8) cta_radix_sort_depth<(MAXI >= 16 ? 8 : 1)>(skey, whist, bin_base, &s_flag);
+            else if (MAXI >= 16 && items == 16) cta_radix_sort_depth<(MAXI >= 16 ? 16 : 1)>(skey, whist, bin_base, &s_flag);
+            else if (MAXI >= 64 && items == 32) cta_radix_sort_depth<(MAXI >= 64 ? 32 : 1)>(skey, whist, bin_base, &s_flag);
+            else if (MAXI >= 64) cta_radix_sort_depth<(MAXI >= 64 ? 64 : 1)>(skey, whist, bin_base, &s_flag);
+            // tie fix-up: the thread at the start of a run of equal depths insertion-sorts the run by k
+            for (int i = threadIdx.x; i < L; i += blockDim.x) {
+                const unsigned dep = (unsigned)(skey[i] >> 32);
+                if (i > 0 && (unsigned)(skey[i - 1] >> 32) == dep) continue;   // not a run start
+                int e = i + 1;
+                while (e < L && (unsigned)(skey[e] >> 32) == dep) ++e;
+                for (int p = i + 1; p < e; ++p) {
+                    const u64 v = skey[p];
+                    int q = p - 1;
+                    while (q >= i && skey[q] > v) { skey[q + 1] = skey[q]; --q; }
+                    skey[q + 1] = v;
+                }
+            }
         }
         __syncthreads();
-        for (int k = 128; k <= n2; k <<= 1) {
-            for (int j = k >> 1; j >= 64; j >>= 1) {  // wide strides through shared memory
-                for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int hiI = lo + j;
-                    const bool asc = ((lo & k) == 0);
-                    const u64 x = skey[lo], y = skey[hiI];
-                    if ((x > y) == asc) {
-                        skey[lo] = y;
-                        skey[hiI] = x;
-                    }
-                }
-                __syncthreads();
-            }
-            for (int blk = warp; blk < nblk; blk += nwarps) {  // strides 32..1 in registers
-                const int base = blk << 6;
-                u64 a = skey[base + lane], b = skey[base + 32 + lane];
-                block64_substages(a, b, base, lane, k, 32);
-                skey[base + lane] = a;
-                skey[base + 32 + lane] = b;
-            }
-            __syncthreads();
-        }
     }
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const int k = (int)(unsigned)(skey[i] & 0xffffffffull);
@@ -290,6 +367,7 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
     }
     int cap = 64;
     while (cap < max_tile_len) cap <<= 1;
+    if (cap > 64 && cap < 256) cap = 256;
     if (cap > BUCKET_MAX_CAP) {
         gsb_set_error(GSB_ERR_UNSUPPORTED, "tile list longer than the in-shared-memory sort capacity; "
                       "use the generic gsb_sort_intersects path", __FILE__, __LINE__);
@@ -302,12 +380,19 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
     bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, reinterpret_cast<const float2 *>(xys), depths, radii,
                                                          cum_tiles_hit, tiles_x, tiles_y, tile_cursor, comp, gids);
     const size_t smem = (size_t)cap * 8;
-    if (smem > 48 * 1024)
-        GSB_CUDA(cudaFuncSetAttribute(tile_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tile_sort_pack_kernel<<<T, 256, smem, s>>>(cap, reinterpret_cast<const int2 *>(tile_bins), comp, gids,
-                                              reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
-                                              reinterpret_cast<GsbRecord *>(records), sorted_index,
-                                              gaussian_ids_sorted);
+#define GSB_TSP(MAXI)                                                                                           \
+    do {                                                                                                        \
+        if (smem > 38 * 1024)                                                                                   \
+            GSB_CUDA(cudaFuncSetAttribute(tile_sort_pack_kernel<MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                          \
+        tile_sort_pack_kernel<MAXI><<<T, 256, smem, s>>>(                                                       \
+            cap, reinterpret_cast<const int2 *>(tile_bins), comp, gids, reinterpret_cast<const float2 *>(xys),   \
+            conics, colors, opacities, reinterpret_cast<GsbRecord *>(records), sorted_index, gaussian_ids_sorted); \
+    } while (0)
+    if (cap <= 1024) GSB_TSP(4);
+    else if (cap <= 4096) GSB_TSP(16);
+    else GSB_TSP(64);
+#undef GSB_TSP
     GSB_LAUNCH_CHECK();
     return 0;
 }
