@@ -120,6 +120,10 @@ bucket_emit_kernel(int n, const float2 *__restrict__ xys, const float *__restric
 
 typedef unsigned long long u64;
 
+#ifndef GSB_BITONIC_MAX
+#define GSB_BITONIC_MAX 4096   // lists up to this (padded) length use the bitonic network (measured faster), longer ones the radix sort
+#endif
+
 __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
     unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
     lo = __shfl_xor_sync(0xffffffffu, lo, m);
@@ -261,6 +265,41 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
                 for (int k = 2; k <= 64; k <<= 1) block64_substages(a, b, 0, lane, k, k >> 1);
                 skey[lane] = a;
                 skey[32 + lane] = b;
+            }
+        } else if (n2 <= GSB_BITONIC_MAX) {
+            // medium lists: bitonic network, <= 64-wide merges in registers / shuffles, wider strides in smem
+            const int nwarps = blockDim.x >> 5, nblk = n2 >> 6;
+            for (int blk = warp; blk < nblk; blk += nwarps) {
+                const int base = blk << 6;
+                u64 a = skey[base + lane], b = skey[base + 32 + lane];
+#pragma unroll
+                for (int k = 2; k <= 64; k <<= 1) block64_substages(a, b, base, lane, k, k >> 1);
+                skey[base + lane] = a;
+                skey[base + 32 + lane] = b;
+            }
+            __syncthreads();
+            for (int k = 128; k <= n2; k <<= 1) {
+                for (int j = k >> 1; j >= 64; j >>= 1) {
+                    for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int hiI = lo + j;
+                        const bool asc = ((lo & k) == 0);
+                        const u64 x = skey[lo], y = skey[hiI];
+                        if ((x > y) == asc) {
+                            skey[lo] = y;
+                            skey[hiI] = x;
+                        }
+                    }
+                    __syncthreads();
+                }
+                for (int blk = warp; blk < nblk; blk += nwarps) {
+                    const int base = blk << 6;
+                    u64 a = skey[base + lane], b = skey[base + 32 + lane];
+                    block64_substages(a, b, base, lane, k, 32);
+                    skey[base + lane] = a;
+                    skey[base + 32 + lane] = b;
+                }
+                __syncthreads();
             }
         } else {
             const int items = n2 >> 8;
