@@ -195,19 +195,35 @@ sh_backward_multiview_kernel(int n, int degrees_to_use, const float *__restrict_
         float row[S];
 #pragma unroll
         for (int j = 0; j < S; ++j) row[j] = 0.f;
-        for (int r = 0; r < num_views; ++r) {
-            const float *vr = v_rgb_views[r];  // local or peer-mapped (NVLink) pointer
-            const float v0 = vr[3 * g], v1 = vr[3 * g + 1], v2 = vr[3 * g + 2];
-            if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;  // Gaussian not visible in view r
-            float Y[K];
-            sh_basis(nb, mx - __ldg(cam_pos + 3 * r), my - __ldg(cam_pos + 3 * r + 1),
-                     mz - __ldg(cam_pos + 3 * r + 2), Y);
+        // views are processed in groups of 8 whose (peer, NVLink) loads are all issued before any use:
+        // remote-load latency (~2-3 us) is paid once per group, not once per view
+        for (int r0 = 0; r0 < num_views; r0 += 8) {
+            float vv[8][3];
 #pragma unroll
-            for (int b = 0; b < K; ++b) {
-                if (b < nb) {
-                    row[3 * b] = fmaf(Y[b], v0, row[3 * b]);
-                    row[3 * b + 1] = fmaf(Y[b], v1, row[3 * b + 1]);
-                    row[3 * b + 2] = fmaf(Y[b], v2, row[3 * b + 2]);
+            for (int u = 0; u < 8; ++u) {
+                vv[u][0] = vv[u][1] = vv[u][2] = 0.f;
+                if (r0 + u < num_views) {
+                    const float *vr = v_rgb_views[r0 + u];  // local or peer-mapped (NVLink) pointer
+                    vv[u][0] = vr[3 * g];
+                    vv[u][1] = vr[3 * g + 1];
+                    vv[u][2] = vr[3 * g + 2];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float v0 = vv[u][0], v1 = vv[u][1], v2 = vv[u][2];
+                if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;  // not visible in this view (or no view)
+                const int r = r0 + u;
+                float Y[K];
+                sh_basis(nb, mx - __ldg(cam_pos + 3 * r), my - __ldg(cam_pos + 3 * r + 1),
+                         mz - __ldg(cam_pos + 3 * r + 2), Y);
+#pragma unroll
+                for (int b = 0; b < K; ++b) {
+                    if (b < nb) {
+                        row[3 * b] = fmaf(Y[b], v0, row[3 * b]);
+                        row[3 * b + 1] = fmaf(Y[b], v1, row[3 * b + 1]);
+                        row[3 * b + 2] = fmaf(Y[b], v2, row[3 * b + 2]);
+                    }
                 }
             }
         }

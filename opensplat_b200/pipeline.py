@@ -61,6 +61,7 @@ class SplatPipeline:
         self.total_dev = torch.zeros(2, dtype=i32, device=d)
         self.total_host = torch.zeros(2, dtype=i32).pin_memory()
         self.max_len = 0
+        self._m_event = torch.cuda.Event()
         # ---- per-pixel ----
         self.out_img = torch.empty((H, W, 3), dtype=f32, device=d)
         self.final_Ts = torch.empty((H, W), dtype=f32, device=d)
@@ -140,9 +141,6 @@ class SplatPipeline:
         n, W, H = self.n, self.W, self.H
         fx, fy, cx, cy = self.intr
         p = self.p
-        self._stage("sh_fwd")
-        # SH colour with the glue of model.cpp:192 fused: rgbs = clamp_min(colors + 0.5, 0)
-        capi.check(L.gsb_sh_forward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(p["coeffs"]), 0.5, P(self.rgbs), s))
         self._stage("project_fwd")
         capi.check(L.gsb_project_forward(n, P(p["means"]), P(p["scales"]), 1.0, P(p["quats"]), P(self.viewmat),
                                          P(self.projmat), fx, fy, cx, cy, H, W, self.tb[0], self.tb[1], 0.01,
@@ -155,9 +153,15 @@ class SplatPipeline:
         if use_bucket:
             capi.check(L.gsb_bucket_tile_ranges(n, P(self.xys), P(self.radii), self.tb[0], self.tb[1],
                                                 P(self.tile_bins), P(self.tile_cursor), P(self.total_dev), s))
-        # the path's one device->host read-back (rasterize_gaussians.cpp:63): M (+ longest tile list)
+        # the path's one device->host read-back (rasterize_gaussians.cpp:63): M (+ longest tile list).
+        # The host waits on an EVENT recorded right after the copy, and the SH colour pass (independent of the
+        # binning) is enqueued behind it: the GPU stays busy while the host wakes up and enqueues the rest.
         self.total_host.copy_(self.total_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        self._m_event.record()
+        self._stage("sh_fwd")
+        # SH colour with the glue of model.cpp:192 fused: rgbs = clamp_min(colors + 0.5, 0)
+        capi.check(L.gsb_sh_forward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(p["coeffs"]), 0.5, P(self.rgbs), s))
+        self._m_event.synchronize()
         m = int(self.total_host[0])
         self.max_len = int(self.total_host[1]) if use_bucket else 0
         self.m = m
