@@ -42,7 +42,10 @@ __device__ __forceinline__ void zero_row(float *grad_rows, int k) {
     row[0] = z; row[1] = z; row[2] = z;
 }
 
-__global__ void __launch_bounds__(RK_THREADS)
+#ifndef GSB_BWD_MINB
+#define GSB_BWD_MINB 6   // 80 registers -> 6 CTAs per SM (measured)
+#endif
+__global__ void __launch_bounds__(RK_THREADS, GSB_BWD_MINB)
 rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                           const int2 *__restrict__ tile_bins, const GsbRecord *__restrict__ records,
                           const float *__restrict__ background, const float *__restrict__ final_Ts,
@@ -78,14 +81,14 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         // Per pixel only the SCALAR Bq = (colour behind) . v_out - q is tracked instead of the reference's 3-vector
         // `buffer` (backward.cu:200,319-321): v_alpha = sum_c (rgb_c T - buffer_c ra) v_out_c + ra q
         //                                            = T (rgb . v_out) - ra (buffer . v_out - q).
-        float T[RK_PIX], Bq[RK_PIX], py[RK_PIX];
+        float T[RK_PIX], Bq[RK_PIX];
+        const float py0 = (float)Y0;
         float vor[RK_PIX], vog[RK_PIX], vob[RK_PIX];
         int binf[RK_PIX];
         int my_max = -1;
 #pragma unroll
         for (int j = 0; j < RK_PIX; ++j) {
             const int Y = Y0 + 2 * j;
-            py[j] = (float)Y;
             if (X < img_w && Y < img_h) {
                 const size_t p = (size_t)Y * img_w + X;
                 const float Tf = final_Ts[p];
@@ -152,13 +155,14 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 const float dx = q0.x - px;
                 const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
                 const float bdx = q1.y * dx;
+                const float dy0 = q0.y - py0;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f;  // sum w, sum w dy, sum w dy^2 over this lane's pixels
                 float a_r = 0.f, a_g = 0.f, a_b = 0.f;
                 bool any = false;
                 const int jlo = __ffs(rm) - 1, jhi = 31 - __clz(rm);   // slots inside the y-extent (contiguous)
 #define GSB_BWD_SLOT(j)                                                                                   \
     {                                                                                                     \
-        const float dy = q0.y - py[j];                                                                    \
+        const float dy = dy0 - (float)(2 * j);  /* centre.y - pixel row */                                                                    \
         const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);                                          \
         if (__float_as_uint(sigma) <= __float_as_uint(smax)) { /* 0 <= sigma <= smax */                   \
             const float au = ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z)); /* opac * exp(-sigma) */          \
