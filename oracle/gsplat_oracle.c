@@ -462,7 +462,6 @@ void orc_sort_isects(int64_t m, const int64_t *keys, int64_t *keys_sorted, int32
             int64_t mid = lo + w < m ? lo + w : m, hi = lo + 2 * w < m ? lo + 2 * w : m;
             int64_t a = lo, b = mid, o = lo;
             while (a < mid && b < hi) {
-                if (kb == NULL) break;
                 if (ka[b] < ka[a]) { kb[o] = ka[b]; ib[o++] = ia[b++]; }
                 else               { kb[o] = ka[a]; ib[o++] = ia[a++]; }
             }
