@@ -396,6 +396,59 @@ def test_one_gaussian_covering_every_tile():
     assert ok, stats
 
 
+@pytest.mark.parametrize("n,expect_path", [(6000, "radix"), (20000, "generic")])
+def test_very_long_tile_lists_take_radix_and_generic_paths(n, expect_path):
+    """All Gaussians piled on one spot: a tile list longer than the bitonic (4096) / in-smem (16384) limits.
+    The operator must still match the oracle (CTA radix sort, resp. the generic global radix sort fallback)."""
+    from opensplat_b200 import capi
+    W, H = 64, 48
+    sc = _scene(n, W, H, 0.05, opacity=(0.002, 0.01), seed=n)
+    sc["means"][:, 0] = sc["means"][:, 0] * 0.05          # pile up around the image centre
+    sc["means"][:, 1] = sc["means"][:, 1] * 0.05
+    rng = np.random.default_rng(1)
+    colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    tb = ops.tile_bounds(W, H)
+    bins, cursor, stats = ops.bucket_tile_ranges(xys, radii, tb)
+    m, max_len = (int(v) for v in stats.tolist())
+    cap = capi.lib().gsb_bucket_max_tile_len()
+    assert (max_len > 4096 and max_len <= cap) if expect_path == "radix" else (max_len > cap)
+    colt, opt = cu(colors).requires_grad_(), cu(sc["opacities"]).requires_grad_()
+    bg = cu(np.array([0.1, 0.2, 0.3], np.float32))
+    img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, colt, opt, H, W, bg)
+    o = _project_orc(sc)
+    cum, _ = orc.cumsum(o["num_tiles_hit"])
+    b = orc.bin_and_sort(o["xys"], o["depths"], o["radii"], cum, H, W)
+    f = orc.rasterize_forward(H, W, b["gaussian_ids_sorted"], b["tile_bins"], o["xys"], o["conics"], colors,
+                              sc["opacities"], [0.1, 0.2, 0.3], exp_mode=1)
+    ok, stats_ = image_close(npy(img), f["out_img"], tol=2e-5, frac=2e-3)
+    assert ok, stats_
+    wgt = rng.uniform(-1, 1, (H, W, 3)).astype(np.float32)
+    (img * cu(wgt)).sum().backward()
+    r = orc.rasterize_backward(H, W, b["gaussian_ids_sorted"], b["tile_bins"], o["xys"], o["conics"], colors,
+                               sc["opacities"], [0.1, 0.2, 0.3], f["final_Ts"], f["final_idx"], wgt, exp_mode=1)
+    assert rel_l2(npy(colt.grad), r["v_colors"]) <= 1e-3 and rel_l2(npy(opt.grad), r["v_opacity"]) <= 1e-3
+
+
+def test_dense_overlap_parity_c5_like():
+    """Config C5 in miniature: ~200 candidate splats per pixel, saturating tiles, long lists (bitonic 2048-4096)."""
+    n, W, H = 60_000, 320, 192
+    sc = _scene(n, W, H, 0.16, opacity=(0.05, 0.95), seed=55)
+    rng = np.random.default_rng(2)
+    colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    (out, fT, fI), o, st = _raster_both(sc, colors, [0, 0, 0])
+    assert st["m"] / (W * H / 256) > 1000          # > 1000 records per tile on average
+    ok, stats = image_close(npy(out), o["out_img"], tol=2e-5, frac=2e-3)
+    assert ok, stats
+    wgt = rng.uniform(-1, 1, (H, W, 3)).astype(np.float32)
+    v = ops.rasterize_backward(H, W, n, st["m"], st["bins"], st["conics"], cu(sc["opacities"]), st["rec"], st["cum"],
+                               st["bg"], cu(o["final_Ts"]), cu(o["final_idx"]), cu(wgt))
+    ob = orc.rasterize_backward(H, W, npy(st["gs"]), npy(st["bins"]), npy(st["xys"]), npy(st["conics"]), colors,
+                                sc["opacities"], [0, 0, 0], o["final_Ts"], o["final_idx"], wgt, exp_mode=1)
+    for a, b in zip(v, (ob["v_xy"], ob["v_conic"], ob["v_colors"], ob["v_opacity"])):
+        assert rel_l2(npy(a), b) <= 2e-3
+
+
 # ---------------------------------------------------------------- full-size properties (config C2)
 @pytest.mark.parametrize("n,W,H,scale", [(1_000_000, 1920, 1080, 0.02)])
 def test_full_size_properties_and_oracle(n, W, H, scale):
