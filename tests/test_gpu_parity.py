@@ -432,7 +432,7 @@ def test_very_long_tile_lists_take_radix_and_generic_paths(n, expect_path):
 
 def test_dense_overlap_parity_c5_like():
     """Config C5 in miniature: ~200 candidate splats per pixel, saturating tiles, long lists (bitonic 2048-4096)."""
-    n, W, H = 60_000, 320, 192
+    n, W, H = 100_000, 320, 192
     sc = _scene(n, W, H, 0.16, opacity=(0.05, 0.95), seed=55)
     rng = np.random.default_rng(2)
     colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
