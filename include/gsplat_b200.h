@@ -197,6 +197,16 @@ int gsb_adam_step(long long n, float *param, const float *grad, float *exp_avg, 
                   float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
                   gsb_stream_t stream);
 
+/* gsb_ssim_l1_loss: the training loss of Model::mainLoss (model.cpp:780-784): (1-w) * mean|rendered - gt| +
+ *   w * (1 - SSIM(rendered, gt)) with the reference's SSIM (ssim.cpp:8-47: 11x11 window gaussian(1.5) evaluated
+ *   at floor((i-11)/2), zero padding 5, C1 = 1e-4, C2 = 9e-4, mean over all channels) and its gradient w.r.t.
+ *   `rendered`, fused into two tile kernels.  rendered / gt / v_rendered are [H,W,3] channels-last;
+ *   loss_out is a device float[3] = {total, L1, SSIM}; workspace of gsb_ssim_workspace_bytes(H, W). */
+size_t gsb_ssim_workspace_bytes(int img_h, int img_w);
+int gsb_ssim_l1_loss(int img_h, int img_w, const float *rendered, const float *gt, float ssim_weight,
+                     float *v_rendered, float *loss_out, void *workspace, size_t workspace_bytes,
+                     gsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ SOURCES = {
     "raster_fwd.cu": [],
     "raster_bwd.cu": [],
     "fused.cu": [],
+    "ssim.cu": [],
 }
 
 

@@ -343,3 +343,30 @@ class SphericalHarmonics(torch.autograd.Function):
         degreesToUse, degree = ctx.meta
         (viewDirs,) = ctx.saved_tensors
         return None, None, compute_sh_backward(degree, degreesToUse, viewDirs, v_colors.contiguous())
+
+
+class MainLoss(torch.autograd.Function):
+    """Model::mainLoss (model.cpp:780-784): (1 - w) * L1 + w * (1 - SSIM), fused forward + gradient
+    (gsb_ssim_l1_loss).  rendered, gt: [H,W,3] CUDA tensors.  Returns the scalar loss."""
+
+    @staticmethod
+    def forward(ctx, rendered, gt, ssimWeight):
+        H, W = rendered.shape[0], rendered.shape[1]
+        if rendered.dim() != 3 or rendered.shape[2] != 3 or gt.shape != rendered.shape:
+            raise ValueError("rendered and gt must be [H,W,3]")
+        L = capi.lib()
+        r, g = capi.f32(rendered), capi.f32(gt)
+        ws = _ws.get(r.device, "ssim", L.gsb_ssim_workspace_bytes(H, W) + 256)
+        off = (-ws.data_ptr()) % 256
+        v = torch.empty_like(r)
+        out = torch.empty(3, dtype=torch.float32, device=r.device)
+        capi.check(L.gsb_ssim_l1_loss(H, W, capi.ptr(r), capi.ptr(g), float(ssimWeight), capi.ptr(v), capi.ptr(out),
+                                      ws.data_ptr() + off, ws.numel() - off, capi.stream()))
+        ctx.save_for_backward(v)
+        ctx.parts = out
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, v_loss):
+        (v,) = ctx.saved_tensors
+        return v * v_loss, None, None

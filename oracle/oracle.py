@@ -162,3 +162,45 @@ def rasterize_backward(img_h, img_w, gaussian_ids_sorted, tile_bins, xys, conics
                                  _fp(colors), _fp(opac), _fp(bg), _fp(fT), _fp(fI), _fp(vo), _fp(voa),
                                  int(exp_mode), n, _fp(v_xy), _fp(v_conic), _fp(v_col), _fp(v_op))
     return dict(v_xy=v_xy, v_conic=v_conic, v_colors=v_col, v_opacity=v_op)
+
+
+# ------------------------------------------------------------------------------------------------
+# Training loss: Model::mainLoss model.cpp:780-784 = (1-w) * l1 + w * (1 - SSIM), with
+# SSIM::eval ssim.cpp:8-32, window ssim.cpp:34-47 (gaussian(1.5) at floor((i-11)/2), normalised), zero padding 5,
+# l1 model.cpp:54-56.  numpy/scipy restatement in float64 with the analytic gradient w.r.t. `rendered`.
+# ------------------------------------------------------------------------------------------------
+def ssim_window():
+    i = np.arange(11, dtype=np.float32)
+    d = np.floor((i - 11.0) / 2.0).astype(np.float32)
+    g = np.exp(-(d ** 2) / np.float32(2.0 * 1.5 * 1.5)).astype(np.float32)
+    return (g / g.sum()).astype(np.float64)
+
+
+def main_loss(rendered, gt, ssim_weight):
+    """rendered, gt: [H,W,3].  Returns dict(loss, l1, ssim, v_rendered)."""
+    from scipy.ndimage import correlate1d
+    w = ssim_window()
+    y = np.asarray(rendered, np.float64)
+    x = np.asarray(gt, np.float64)
+
+    def filt(a, k):  # conv2d(padding=5) of the reference == separable cross-correlation, zero padded
+        a = correlate1d(a, k, axis=0, mode="constant", cval=0.0)
+        return correlate1d(a, k, axis=1, mode="constant", cval=0.0)
+
+    mx, my = filt(x, w), filt(y, w)
+    sxx, syy, sxy = filt(x * x, w) - mx * mx, filt(y * y, w) - my * my, filt(x * y, w) - mx * my
+    C1, C2 = np.float32(0.01 * 0.01), np.float32(0.03 * 0.03)
+    A1, A2 = 2 * mx * my + C1, 2 * sxy + C2
+    B1, B2 = mx * mx + my * my + C1, sxx + syy + C2
+    S = A1 * A2 / (B1 * B2)
+    count = y.size
+    ssim = S.mean()
+    l1 = np.abs(x - y).mean()
+    loss = (1 - ssim_weight) * l1 + ssim_weight * (1 - ssim)
+    d_e12 = 2 * A1 / (B1 * B2)
+    d_e22 = -S / B2
+    d_mu = 2 * mx * (A2 - A1) / (B1 * B2) - 2 * my * S / B1 + 2 * my * S / B2
+    wt = w[::-1].copy()  # transposed (adjoint) filter
+    dssim = filt(d_mu, wt) + 2 * y * filt(d_e22, wt) + x * filt(d_e12, wt)
+    v = -ssim_weight / count * dssim + (1 - ssim_weight) / count * np.sign(y - x)
+    return dict(loss=float(loss), l1=float(l1), ssim=float(ssim), v_rendered=v.astype(np.float32))

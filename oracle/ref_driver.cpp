@@ -14,6 +14,7 @@
 #include "project_gaussians.hpp"
 #include "rasterize_gaussians.hpp"
 #include "spherical_harmonics.hpp"
+#include "ssim.hpp"
 
 static std::vector<torch::Tensor> ref_project_cpu(
     torch::Tensor means, torch::Tensor scales, double globScale, torch::Tensor quats,
@@ -37,11 +38,22 @@ static torch::Tensor ref_sh_cpu(int64_t degreesToUse, torch::Tensor viewDirs, to
     return SphericalHarmonicsCPU::apply((int)degreesToUse, viewDirs, coeffs);
 }
 
+// Model::mainLoss (model.cpp:780-784) with the reference's own SSIM class (ssim.cpp, compiled unmodified) and
+// its l1 helper (model.cpp:54-56: (rendered - gt).abs().mean()); model.cpp itself needs OpenCV/nanoflann headers
+// that are unavailable offline, so these three lines are restated here around the reference's SSIM::eval.
+static torch::Tensor ref_main_loss_cpu(torch::Tensor rgb, torch::Tensor gt, double ssimWeight) {
+    static SSIM ssim(11, 3);  // model.hpp:32
+    torch::Tensor ssimLoss = 1.0f - ssim.eval(rgb, gt);
+    torch::Tensor l1Loss = (rgb - gt).abs().mean();
+    return (1.0f - (float)ssimWeight) * l1Loss + (float)ssimWeight * ssimLoss;
+}
+
 static int64_t ref_num_threads() { return (int64_t)at::get_num_threads(); }
 
 TORCH_LIBRARY(opensplat_ref, m) {
     m.def("project_cpu", &ref_project_cpu);
     m.def("rasterize_cpu", &ref_rasterize_cpu);
     m.def("sh_cpu", &ref_sh_cpu);
+    m.def("main_loss_cpu", &ref_main_loss_cpu);
     m.def("num_threads", &ref_num_threads);
 }

@@ -73,6 +73,19 @@ def sh_case(name, n, degree, seed):
     print(name, "ok")
 
 
+def loss_case(name, H, W, ssim_weight, seed):
+    """Model::mainLoss (model.cpp:780-784) through the reference's SSIM class (ssim.cpp)."""
+    rng = np.random.default_rng(seed)
+    gt = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    rend = np.clip(gt + 0.15 * rng.standard_normal((H, W, 3)).astype(np.float32), 0, 1).astype(np.float32)
+    r = torch.from_numpy(rend).requires_grad_()
+    loss = ref.ops().main_loss_cpu(r, torch.from_numpy(gt), ssim_weight)
+    loss.backward()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), rendered=rend, gt=gt, ssim_weight=np.array(ssim_weight),
+                        ref_loss=np.array(float(loss.detach())), ref_v_rendered=r.grad.numpy())
+    print(name, "loss", float(loss.detach()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     # tight: low opacity (no D5 fringe), ragged image size (partial tiles), black background
@@ -84,3 +97,4 @@ if __name__ == "__main__":
     chain_case("chain_opaque_96x96", 1500, 96, 96, 0.6, (0.5, 0.95), [0, 0, 0], seed=3)
     sh_case("sh_deg3", 500, 3, seed=4)
     sh_case("sh_deg4", 200, 4, seed=5)
+    loss_case("loss_45x70", 45, 70, 0.2, seed=6)

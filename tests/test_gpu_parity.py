@@ -497,3 +497,28 @@ def test_full_size_properties_and_oracle(n, W, H, scale):
                                  npy(fT), npy(fI), npy(wgt), exp_mode=1)
     for a, b in zip(v, (orb["v_xy"], orb["v_conic"], orb["v_colors"], orb["v_opacity"])):
         assert rel_l2(npy(a), b) <= 1e-3
+
+
+# ------------------------------------------------------------------------ training loss
+def test_main_loss_vs_reference_golden_and_oracle():
+    g = load_golden("loss_45x70")
+    rend = cu(g["rendered"]).requires_grad_()
+    loss = ops.MainLoss.apply(rend, cu(g["gt"]), float(g["ssim_weight"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["ref_loss"])) <= 2e-6                       # vs the reference itself
+    assert rel_l2(npy(rend.grad), g["ref_v_rendered"]) <= 2e-5
+    o = orc.main_loss(g["rendered"], g["gt"], float(g["ssim_weight"]))
+    assert abs(float(loss) - o["loss"]) <= 2e-6 and rel_l2(npy(rend.grad), o["v_rendered"]) <= 2e-5
+
+
+@pytest.mark.parametrize("H,W,w", [(16, 16, 0.2), (33, 50, 0.5), (270, 480, 0.2), (5, 7, 1.0)])
+def test_main_loss_ragged_sizes_vs_oracle(H, W, w):
+    rng = np.random.default_rng(H * W)
+    gt = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    rend = np.clip(gt + 0.2 * rng.standard_normal((H, W, 3)), 0, 1).astype(np.float32)
+    r = cu(rend).requires_grad_()
+    loss = ops.MainLoss.apply(r, cu(gt), w)
+    (3.0 * loss).backward()
+    o = orc.main_loss(rend, gt, w)
+    assert abs(float(loss) - o["loss"]) <= 5e-6
+    assert rel_l2(npy(r.grad), 3.0 * o["v_rendered"]) <= 5e-5

@@ -113,3 +113,14 @@ def test_tile_semantics_edge_cases():
     b = orc.bin_and_sort(p["xys"], p["depths"], p["radii"], cum, H, W)
     assert np.all((b["isect_ids"] & 0xFFFFFFFF) == np.float32(2.0).view(np.int32))
     assert np.all(np.diff(b["isect_ids_sorted"]) >= 0)
+
+
+def test_main_loss_matches_reference():
+    """(1-w) L1 + w (1 - SSIM) and its gradient: numpy restatement vs the reference's SSIM class + autograd."""
+    g = load_golden("loss_45x70")
+    r = orc.main_loss(g["rendered"], g["gt"], float(g["ssim_weight"]))
+    assert abs(r["loss"] - float(g["ref_loss"])) <= 1e-6
+    assert rel_l2(r["v_rendered"], g["ref_v_rendered"]) <= 1e-5
+    # the reference's window is the asymmetric staircase of ssim.cpp:41-47, not a centred Gaussian
+    w = orc.ssim_window()
+    assert abs(w.sum() - 1) < 1e-6 and w[10] > w[0] and abs(w[9] - w[10]) < 1e-12 and w[0] != w[10]
