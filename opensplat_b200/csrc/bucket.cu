@@ -45,7 +45,8 @@ tile_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__
         for (int tx = x0; tx < x1; ++tx) atomicAdd(&tile_count[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
 }
 
-// single CTA: exclusive scan of tile_count -> tile_bins; zeroes the cursors; max tile length
+// single CTA: exclusive scan of tile_count -> tile_bins, write cursors, max tile length.
+// Each thread owns 8 consecutive tiles per trip (all 8 strided loads issued before use).
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int T, int *__restrict__ tile_count_then_cursor, int2 *__restrict__ tile_bins,
                  int *__restrict__ stats /* [0] = total, [1] = max length */) {
@@ -55,11 +56,15 @@ tile_scan_kernel(int T, int *__restrict__ tile_count_then_cursor, int2 *__restri
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
     int carry = 0, my_max = 0;
-    for (int base = 0; base < T; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = (i < T) ? tile_count_then_cursor[(size_t)i * CUR_STRIDE] : 0;
-        my_max = max(my_max, v);
-        int inc = v;
+    for (int base = 0; base < T; base += 8192) {
+        const int i0 = base + threadIdx.x * 8;
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (i0 + k < T) ? tile_count_then_cursor[(size_t)(i0 + k) * CUR_STRIDE] : 0;
+        int tsum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tsum += v[k]; my_max = max(my_max, v[k]); }
+        int inc = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -79,11 +84,15 @@ tile_scan_kernel(int T, int *__restrict__ tile_count_then_cursor, int2 *__restri
             if (lane == 31) sm[32] = xi;
         }
         __syncthreads();
-        const int excl = carry + sm[w] + inc - v;
-        if (i < T) {
-            // empty tiles keep (0,0) like the reference's zero-initialised tile_bins
-            tile_bins[i] = (v > 0) ? make_int2(excl, excl + v) : make_int2(0, 0);
-            tile_count_then_cursor[(size_t)i * CUR_STRIDE] = excl;   // becomes the write cursor of K3
+        int excl = carry + sm[w] + inc - tsum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < T) {
+                // empty tiles keep (0,0) like the reference's zero-initialised tile_bins
+                tile_bins[i0 + k] = (v[k] > 0) ? make_int2(excl, excl + v[k]) : make_int2(0, 0);
+                tile_count_then_cursor[(size_t)(i0 + k) * CUR_STRIDE] = excl;  // becomes the write cursor of K3
+            }
+            excl += v[k];
         }
         carry += sm[32];
         __syncthreads();

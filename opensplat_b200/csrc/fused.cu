@@ -50,9 +50,24 @@ adam_kernel(long long n4, long long n, float *__restrict__ p, const float *__res
         mm = b1 * mm + (1.f - b1) * gg;
         vv = b2 * vv + (1.f - b2) * gg * gg;
         // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-        pp -= lr * inv_bc1 * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+        pp -= lr * inv_bc1 * __fdividef(mm, sqrtf(vv) * inv_sqrt_bc2 + eps);
     };
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    // two float4 per thread per trip: 8 independent 128-bit loads in flight before the first use
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {
+        const long long j = i + stride;
+        float4 P0 = reinterpret_cast<float4 *>(p)[i], P1 = reinterpret_cast<float4 *>(p)[j];
+        const float4 G0 = ldg_stream4(reinterpret_cast<const float4 *>(g) + i);
+        const float4 G1 = ldg_stream4(reinterpret_cast<const float4 *>(g) + j);
+        float4 M0 = reinterpret_cast<float4 *>(m)[i], M1 = reinterpret_cast<float4 *>(m)[j];
+        float4 V0 = reinterpret_cast<float4 *>(v)[i], V1 = reinterpret_cast<float4 *>(v)[j];
+        upd(P0.x, G0.x, M0.x, V0.x); upd(P0.y, G0.y, M0.y, V0.y); upd(P0.z, G0.z, M0.z, V0.z); upd(P0.w, G0.w, M0.w, V0.w);
+        upd(P1.x, G1.x, M1.x, V1.x); upd(P1.y, G1.y, M1.y, V1.y); upd(P1.z, G1.z, M1.z, V1.z); upd(P1.w, G1.w, M1.w, V1.w);
+        reinterpret_cast<float4 *>(p)[i] = P0; reinterpret_cast<float4 *>(p)[j] = P1;
+        reinterpret_cast<float4 *>(m)[i] = M0; reinterpret_cast<float4 *>(m)[j] = M1;
+        reinterpret_cast<float4 *>(v)[i] = V0; reinterpret_cast<float4 *>(v)[j] = V1;
+    }
+    for (; i < n4; i += stride) {
         float4 P = reinterpret_cast<float4 *>(p)[i];
         const float4 G = ldg_stream4(reinterpret_cast<const float4 *>(g) + i);
         float4 M = reinterpret_cast<float4 *>(m)[i];

@@ -522,3 +522,36 @@ def test_main_loss_ragged_sizes_vs_oracle(H, W, w):
     o = orc.main_loss(rend, gt, w)
     assert abs(float(loss) - o["loss"]) <= 5e-6
     assert rel_l2(npy(r.grad), 3.0 * o["v_rendered"]) <= 5e-5
+
+
+def test_fused_adam_matches_torch_adam():
+    from opensplat_b200 import capi
+    torch.manual_seed(0)
+    n = 1_000_003
+    p0 = torch.randn(n, device=DEV)
+    p_ref = p0.clone().requires_grad_()
+    opt = torch.optim.Adam([p_ref], lr=1e-2, foreach=False)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    L = capi.lib()
+    for t in range(1, 6):
+        g = torch.randn(n, device=DEV) * (0.1 * t)
+        p_ref.grad = g.clone()
+        opt.step()
+        capi.check(L.gsb_adam_step(n, capi.ptr(p), capi.ptr(g), capi.ptr(m), capi.ptr(v), 1e-2, 0.9, 0.999, 1e-8,
+                                   1 - 0.9 ** t, 1 - 0.999 ** t, capi.stream()))
+    assert float((p - p_ref.detach()).abs().max()) <= 2e-6
+
+
+def test_mse_loss_grad_matches_torch():
+    from opensplat_b200 import capi
+    H, W = 123, 77
+    img = torch.rand(H, W, 3, device=DEV).requires_grad_()
+    tgt = torch.rand(H, W, 3, device=DEV)
+    ref = torch.nn.functional.mse_loss(img, tgt)
+    ref.backward()
+    v = torch.empty_like(tgt)
+    loss = torch.full((1,), 7.0, device=DEV)   # the call must overwrite, not accumulate onto stale values
+    cnt = H * W * 3
+    capi.check(capi.lib().gsb_mse_loss_grad(cnt, capi.ptr(img.detach()), capi.ptr(tgt), capi.ptr(v), capi.ptr(loss),
+                                            1.0 / cnt, capi.stream()))
+    assert abs(float(loss) - float(ref)) <= 1e-6 and float((v - img.grad).abs().max()) <= 1e-9
