@@ -27,11 +27,13 @@ WORKLOADS = {
     "c5_5M_1440p_dense": (5_000_000, 2560, 1440, 0.023, (0.05, 0.95)),   # ~200 blended-candidate splats / pixel
     "c1_1k_256": (1_000, 256, 256, 0.5, (0.05, 0.95)),
 }
-# kernels of OURS launched per fwd+bwd step (counted from the C-ABI implementations):
-#   sh_fwd 1, project_fwd 1, scan 3, emit 1, sort 2 + passes, gather/bins 1, pack 1, blend_fwd 1,
-#   mse 1, blend_bwd 1, row_reduce 1, project_bwd 1, sh_bwd 1
-def launches_per_step(passes, train=False):
-    return 1 + 1 + 3 + 1 + (2 + passes) + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + (1 if train else 0)
+# kernels of OURS launched per fwd+bwd step (counted from the C-ABI implementations, bucket fast path):
+#   project_fwd 1, cumsum 3, tile_count 1, tile_scan 1, sh_fwd(+clamp) 1, bucket_emit 1, tile_sort_pack 1,
+#   blend_fwd 1, mse 1, blend_bwd 1, row_reduce 1, project_bwd 1, sh_bwd 1 (N>1 fused exchange: mask 1 + multiview 1)
+def launches_per_step(world=1, fused=True, train=False):
+    n = 1 + 3 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1
+    n += 2 if (world > 1 and fused) else 1
+    return n + (1 if train else 0)
 
 
 class ClockSampler:
@@ -343,7 +345,7 @@ def run_ours(args):
                 "api": ("C++ libtorch autograd operators ProjectGaussians/RasterizeGaussians/SphericalHarmonics "
                         "(libopensplat_b200_ops.so via torch.ops)") if use_cpp else
                        "opensplat_b200.ops python autograd operators"},
-        "gpu_launches": launches_per_step(passes) * args.steps,
+        "gpu_launches": launches_per_step(world, args.exchange == "fused") * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_key, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
