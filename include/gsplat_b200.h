@@ -197,6 +197,17 @@ int gsb_adam_step(long long n, float *param, const float *grad, float *exp_avg, 
                   float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
                   gsb_stream_t stream);
 
+/* gsb_activate_forward / gsb_activate_backward: the parameter activations of Model::forward fused into one
+ *   pass each way (model.cpp:148-150,176-177,200): scales = exp(log_scales), quats = raw_quats / |raw_quats|,
+ *   opacities = sigmoid(opacity_logits), viewdirs = normalize(means - cam_pos) (detached: no gradient).
+ *   cam_pos is a device float[3].  The backward takes the forward outputs (scales, opacities). */
+int gsb_activate_forward(int n, const float *means, const float *log_scales, const float *raw_quats,
+                         const float *opacity_logits, const float *cam_pos, float *scales, float *quats,
+                         float *opacities, float *viewdirs, gsb_stream_t stream);
+int gsb_activate_backward(int n, const float *scales, const float *raw_quats, const float *opacities,
+                          const float *v_scales, const float *v_quats, const float *v_opacities,
+                          float *v_log_scales, float *v_raw_quats, float *v_opacity_logits, gsb_stream_t stream);
+
 /* gsb_ssim_l1_loss: the training loss of Model::mainLoss (model.cpp:780-784): (1-w) * mean|rendered - gt| +
  *   w * (1 - SSIM(rendered, gt)) with the reference's SSIM (ssim.cpp:8-47: 11x11 window gaussian(1.5) evaluated
  *   at floor((i-11)/2), zero padding 5, C1 = 1e-4, C2 = 9e-4, mean over all channels) and its gradient w.r.t.

@@ -81,6 +81,51 @@ adam_kernel(long long n4, long long n, float *__restrict__ p, const float *__res
         upd(p[i], g[i], m[i], v[i]);
 }
 
+// ---- parameter activations of Model::forward (model.cpp:114,148-150,176-177,200), one pass each way ----
+__global__ void __launch_bounds__(256)
+activate_forward_kernel(int n, const float *__restrict__ means, const float *__restrict__ log_scales,
+                        const float *__restrict__ raw_quats, const float *__restrict__ opacity_logits,
+                        const float *__restrict__ cam_pos, float *__restrict__ scales,
+                        float4 *__restrict__ quats, float *__restrict__ opacities, float *__restrict__ viewdirs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    scales[3 * i] = expf(log_scales[3 * i]);
+    scales[3 * i + 1] = expf(log_scales[3 * i + 1]);
+    scales[3 * i + 2] = expf(log_scales[3 * i + 2]);
+    const float4 q = reinterpret_cast<const float4 *>(raw_quats)[i];
+    const float inv = 1.f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    quats[i] = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+    opacities[i] = 1.f / (1.f + expf(-opacity_logits[i]));
+    const float dx = means[3 * i] - __ldg(cam_pos), dy = means[3 * i + 1] - __ldg(cam_pos + 1),
+                dz = means[3 * i + 2] - __ldg(cam_pos + 2);
+    const float dn = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+    viewdirs[3 * i] = dx * dn; viewdirs[3 * i + 1] = dy * dn; viewdirs[3 * i + 2] = dz * dn;
+}
+
+__global__ void __launch_bounds__(256)
+activate_backward_kernel(int n, const float *__restrict__ scales, const float *__restrict__ raw_quats,
+                         const float *__restrict__ opacities, const float *__restrict__ v_scales,
+                         const float4 *__restrict__ v_quats, const float *__restrict__ v_opacities,
+                         float *__restrict__ v_log_scales, float4 *__restrict__ v_raw_quats,
+                         float *__restrict__ v_opacity_logits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // d exp(s) = exp(s)
+    v_log_scales[3 * i] = v_scales[3 * i] * scales[3 * i];
+    v_log_scales[3 * i + 1] = v_scales[3 * i + 1] * scales[3 * i + 1];
+    v_log_scales[3 * i + 2] = v_scales[3 * i + 2] * scales[3 * i + 2];
+    // d (q / |q|) : (I - q^ q^T) / |q|
+    const float4 q = reinterpret_cast<const float4 *>(raw_quats)[i];
+    const float inv = 1.f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    const float4 h = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv), g = v_quats[i];
+    const float dot = h.x * g.x + h.y * g.y + h.z * g.z + h.w * g.w;
+    v_raw_quats[i] = make_float4((g.x - h.x * dot) * inv, (g.y - h.y * dot) * inv, (g.z - h.z * dot) * inv,
+                                 (g.w - h.w * dot) * inv);
+    // d sigmoid = o (1 - o)
+    const float o = opacities[i];
+    v_opacity_logits[i] = v_opacities[i] * o * (1.f - o);
+}
+
 int sm_count() {
     static thread_local int cached = 0;
     if (!cached) {
@@ -120,6 +165,42 @@ extern "C" int gsb_adam_step(long long n, float *param, const float *grad, float
     adam_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(n4, n, param, grad, exp_avg, exp_avg_sq, lr, beta1,
                                                                beta2, eps, 1.f / bias_correction1,
                                                                1.f / sqrtf(bias_correction2));
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Parameter activations of Model::forward fused into one pass: scales = exp(log_scales)
+// (model.cpp:148), quats = raw / |raw| (:150), opacities = sigmoid(logits) (:200), viewdirs =
+// normalize(means - cam_pos) (:176-177; detached, no gradient).  cam_pos is a device float[3].
+extern "C" int gsb_activate_forward(int n, const float *means, const float *log_scales, const float *raw_quats,
+                                    const float *opacity_logits, const float *cam_pos, float *scales, float *quats,
+                                    float *opacities, float *viewdirs, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && cam_pos && scales && quats && opacities &&
+                  viewdirs);
+    GSB_CHECK_ARG(((uintptr_t)raw_quats % 16) == 0 && ((uintptr_t)quats % 16) == 0);
+    activate_forward_kernel<<<gsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        n, means, log_scales, raw_quats, opacity_logits, cam_pos, scales, reinterpret_cast<float4 *>(quats), opacities,
+        viewdirs);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// VJP of gsb_activate_forward: takes the forward OUTPUTS scales / opacities and the raw quaternions.
+extern "C" int gsb_activate_backward(int n, const float *scales, const float *raw_quats, const float *opacities,
+                                     const float *v_scales, const float *v_quats, const float *v_opacities,
+                                     float *v_log_scales, float *v_raw_quats, float *v_opacity_logits,
+                                     gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(scales && raw_quats && opacities && v_scales && v_quats && v_opacities && v_log_scales &&
+                  v_raw_quats && v_opacity_logits);
+    GSB_CHECK_ARG(((uintptr_t)raw_quats % 16) == 0 && ((uintptr_t)v_quats % 16) == 0 &&
+                  ((uintptr_t)v_raw_quats % 16) == 0);
+    activate_backward_kernel<<<gsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        n, scales, raw_quats, opacities, v_scales, reinterpret_cast<const float4 *>(v_quats), v_opacities, v_log_scales,
+        reinterpret_cast<float4 *>(v_raw_quats), v_opacity_logits);
     GSB_LAUNCH_CHECK();
     return 0;
 }

@@ -370,3 +370,36 @@ class MainLoss(torch.autograd.Function):
     def backward(ctx, v_loss):
         (v,) = ctx.saved_tensors
         return v * v_loss, None, None
+
+
+class ActivateGaussians(torch.autograd.Function):
+    """Fused parameter activations of Model::forward (model.cpp:148-150,176-177,200):
+    (means, log_scales, raw_quats, opacity_logits, cam_pos[3]) -> (scales, quats, opacities [N,1], viewdirs)."""
+
+    @staticmethod
+    def forward(ctx, means, log_scales, raw_quats, opacity_logits, cam_pos):
+        n = means.shape[0]
+        means, ls, rq = capi.f32(means), capi.f32(log_scales), capi.f32(raw_quats)
+        ol, cp = capi.f32(opacity_logits).reshape(-1), capi.f32(cam_pos).reshape(3)
+        scales, quats = torch.empty_like(ls), torch.empty_like(rq)
+        opac = torch.empty((n, 1), dtype=torch.float32, device=means.device)
+        vd = torch.empty_like(means)
+        capi.check(capi.lib().gsb_activate_forward(n, capi.ptr(means), capi.ptr(ls), capi.ptr(rq), capi.ptr(ol),
+                                                   capi.ptr(cp), capi.ptr(scales), capi.ptr(quats), capi.ptr(opac),
+                                                   capi.ptr(vd), capi.stream()))
+        ctx.save_for_backward(scales, rq, opac)
+        ctx.mark_non_differentiable(vd)
+        return scales, quats, opac, vd
+
+    @staticmethod
+    def backward(ctx, v_scales, v_quats, v_opac, v_vd):
+        scales, rq, opac = ctx.saved_tensors
+        n = scales.shape[0]
+        z = lambda t, like: capi.f32(t) if t is not None else torch.zeros_like(like)
+        v_scales, v_quats, v_opac = z(v_scales, scales), z(v_quats, rq), z(v_opac, opac)
+        v_ls, v_rq = torch.empty_like(scales), torch.empty_like(rq)
+        v_ol = torch.empty_like(opac)
+        capi.check(capi.lib().gsb_activate_backward(n, capi.ptr(scales), capi.ptr(rq), capi.ptr(opac),
+                                                    capi.ptr(v_scales), capi.ptr(v_quats), capi.ptr(v_opac),
+                                                    capi.ptr(v_ls), capi.ptr(v_rq), capi.ptr(v_ol), capi.stream()))
+        return None, v_ls, v_rq, v_ol, None

@@ -555,3 +555,25 @@ def test_mse_loss_grad_matches_torch():
     capi.check(capi.lib().gsb_mse_loss_grad(cnt, capi.ptr(img.detach()), capi.ptr(tgt), capi.ptr(v), capi.ptr(loss),
                                             1.0 / cnt, capi.stream()))
     assert abs(float(loss) - float(ref)) <= 1e-6 and float((v - img.grad).abs().max()) <= 1e-9
+
+
+def test_fused_activations_match_torch_autograd():
+    """exp / normalize / sigmoid / view directions of Model::forward (model.cpp:148-150,176-177,200)."""
+    torch.manual_seed(1)
+    n = 50_001
+    means = torch.randn(n, 3, device=DEV)
+    ls, rq, ol = (torch.randn(n, k, device=DEV).requires_grad_() for k in (3, 4, 1))
+    cam = torch.tensor([0.3, -0.2, -8.0], device=DEV)
+    s_ref, q_ref, o_ref = torch.exp(ls), rq / rq.norm(2, dim=-1, keepdim=True), torch.sigmoid(ol)
+    vd_ref = (means - cam) / (means - cam).norm(2, dim=-1, keepdim=True)
+    w = [torch.randn_like(t) for t in (s_ref, q_ref, o_ref)]
+    (s_ref * w[0]).sum().add((q_ref * w[1]).sum()).add((o_ref * w[2]).sum()).backward()
+    ref_grads = [t.grad.clone() for t in (ls, rq, ol)]
+    for t in (ls, rq, ol):
+        t.grad = None
+    s, q, o, vd = ops.ActivateGaussians.apply(means, ls, rq, ol, cam)
+    (s * w[0]).sum().add((q * w[1]).sum()).add((o * w[2]).sum()).backward()
+    for a, b in ((s, s_ref), (q, q_ref), (o, o_ref), (vd, vd_ref)):
+        assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(b.abs().max()))
+    for t, gref in zip((ls, rq, ol), ref_grads):
+        assert rel_l2(npy(t.grad), npy(gref)) <= 2e-6
