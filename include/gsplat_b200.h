@@ -208,6 +208,12 @@ int gsb_activate_backward(int n, const float *scales, const float *raw_quats, co
                           const float *v_scales, const float *v_quats, const float *v_opacities,
                           float *v_log_scales, float *v_raw_quats, float *v_opacity_logits, gsb_stream_t stream);
 
+/* gsb_densify_stats_update: the per-step densification statistics of Model::afterTrain (model.cpp:317-337) in
+ *   one pass: for visible Gaussians (radii > 0) xys_grad_norm += |v_xy|, vis_counts += 1,
+ *   max_2d_size = max(max_2d_size, radii / max(H, W)).  All three are [n] fp32, updated in place. */
+int gsb_densify_stats_update(int n, const float *v_xy, const int32_t *radii, int img_h, int img_w,
+                             float *xys_grad_norm, float *vis_counts, float *max_2d_size, gsb_stream_t stream);
+
 /* gsb_ssim_l1_loss: the training loss of Model::mainLoss (model.cpp:780-784): (1-w) * mean|rendered - gt| +
  *   w * (1 - SSIM(rendered, gt)) with the reference's SSIM (ssim.cpp:8-47: 11x11 window gaussian(1.5) evaluated
  *   at floor((i-11)/2), zero padding 5, C1 = 1e-4, C2 = 9e-4, mean over all channels) and its gradient w.r.t.

@@ -126,6 +126,21 @@ activate_backward_kernel(int n, const float *__restrict__ scales, const float *_
     v_opacity_logits[i] = v_opacities[i] * o * (1.f - o);
 }
 
+// ---- densification statistics of Model::afterTrain (model.cpp:317-337), one pass, no boolean-mask indexing ----
+__global__ void __launch_bounds__(256)
+densify_stats_kernel(int n, const float2 *__restrict__ v_xy, const int *__restrict__ radii, float inv_max_hw,
+                     float *__restrict__ xys_grad_norm, float *__restrict__ vis_counts,
+                     float *__restrict__ max_2d_size) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = radii[i];
+    if (r <= 0) return;  // visibleMask = radii > 0
+    const float2 g = v_xy[i];
+    xys_grad_norm[i] += sqrtf(g.x * g.x + g.y * g.y);
+    vis_counts[i] += 1.f;
+    max_2d_size[i] = fmaxf(max_2d_size[i], (float)r * inv_max_hw);
+}
+
 int sm_count() {
     static thread_local int cached = 0;
     if (!cached) {
@@ -201,6 +216,22 @@ extern "C" int gsb_activate_backward(int n, const float *scales, const float *ra
     activate_backward_kernel<<<gsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
         n, scales, raw_quats, opacities, v_scales, reinterpret_cast<const float4 *>(v_quats), v_opacities, v_log_scales,
         reinterpret_cast<float4 *>(v_raw_quats), v_opacity_logits);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Densification statistics (Model::afterTrain model.cpp:317-337): for visible Gaussians
+// (radii > 0): xys_grad_norm += |v_xy|, vis_counts += 1, max_2d_size = max(max_2d_size, radii / max(H, W)).
+// The reference does this with boolean-mask index / index_put (each a host-synchronising nonzero()).
+extern "C" int gsb_densify_stats_update(int n, const float *v_xy, const int32_t *radii, int img_h, int img_w,
+                                        float *xys_grad_norm, float *vis_counts, float *max_2d_size,
+                                        gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && img_h > 0 && img_w > 0);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(v_xy && radii && xys_grad_norm && vis_counts && max_2d_size && ((uintptr_t)v_xy % 8) == 0);
+    const float inv = 1.f / (float)(img_h > img_w ? img_h : img_w);
+    densify_stats_kernel<<<gsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        n, reinterpret_cast<const float2 *>(v_xy), radii, inv, xys_grad_norm, vis_counts, max_2d_size);
     GSB_LAUNCH_CHECK();
     return 0;
 }

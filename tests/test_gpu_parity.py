@@ -577,3 +577,22 @@ def test_fused_activations_match_torch_autograd():
         assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(b.abs().max()))
     for t, gref in zip((ls, rq, ol), ref_grads):
         assert rel_l2(npy(t.grad), npy(gref)) <= 2e-6
+
+
+def test_densify_stats_update_matches_reference_logic():
+    """Model::afterTrain model.cpp:317-337 restated with the same torch ops the reference uses."""
+    from opensplat_b200 import capi
+    torch.manual_seed(2)
+    n, H, W = 20_000, 300, 480
+    v_xy = torch.randn(n, 2, device=DEV)
+    radii = torch.randint(-1, 40, (n,), device=DEV, dtype=torch.int32)
+    gn, vc, ms = torch.rand(n, device=DEV), torch.rand(n, device=DEV).round(), torch.rand(n, device=DEV) * 0.05
+    gn_r, vc_r, ms_r = gn.clone(), vc.clone(), ms.clone()
+    vis = (radii > 0).flatten()
+    grads = torch.linalg.vector_norm(v_xy, 2, dim=-1)
+    vc_r[vis] = vc_r[vis] + 1
+    gn_r[vis] = grads[vis] + gn_r[vis]
+    ms_r[vis] = torch.maximum(ms_r[vis], radii[vis] / float(max(H, W)))
+    capi.check(capi.lib().gsb_densify_stats_update(n, capi.ptr(v_xy), capi.ptr(radii), H, W, capi.ptr(gn), capi.ptr(vc),
+                                                   capi.ptr(ms), capi.stream()))
+    assert torch.allclose(gn, gn_r, rtol=1e-6, atol=1e-7) and torch.equal(vc, vc_r) and torch.allclose(ms, ms_r, rtol=1e-6)

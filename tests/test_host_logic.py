@@ -1,0 +1,47 @@
+"""CPU-only host logic: workspace size queries of the C ABI (no kernel launches), the synthetic scene generator,
+the flat parameter layout."""
+import numpy as np
+
+from opensplat_b200 import capi, parallel
+from opensplat_b200.scene import make_scene, rotated_camera
+
+
+def test_workspace_queries_are_monotone_and_aligned():
+    L = capi.lib()
+    for fn in (L.gsb_sort_workspace_bytes, L.gsb_raster_records_bytes, L.gsb_raster_grad_rows_bytes,
+               L.gsb_bucket_workspace_bytes, L.gsb_cumsum_workspace_bytes):
+        prev = 0
+        for m in (0, 1, 100, 2048, 2049, 1_000_000, 50_000_000):
+            b = fn(m)
+            assert b >= prev and b % 256 == 0
+            prev = b
+    assert L.gsb_raster_records_bytes(1000) >= 1000 * 48 + 256        # 48-B records + the scratch words
+    assert L.gsb_raster_grad_rows_bytes(1000) >= 1000 * 48
+    assert L.gsb_bucket_cursor_bytes(8160) == 8160 * 128              # one 128-B line per tile
+    assert L.gsb_bucket_max_tile_len() == 16384
+    assert L.gsb_ssim_workspace_bytes(1080, 1920) >= 3 * 1080 * 1920 * 3 * 4
+
+
+def test_scene_generator_conventions():
+    sc = make_scene(5000, 320, 200, scale=0.1, sh_degree=3, seed=3)
+    tz = sc["means"][:, 2] + np.float32(8.0)
+    assert len(np.unique(tz)) == 5000                       # strictly distinct view depths
+    assert tz.min() >= 7.0 and tz.max() <= 9.0
+    assert np.allclose(np.linalg.norm(sc["quats"], axis=-1), 1, atol=1e-6)
+    assert np.allclose(np.linalg.norm(sc["viewdirs"], axis=-1), 1, atol=1e-6)
+    assert sc["coeffs"].shape == (5000, 16, 3) and sc["opacities"].shape == (5000, 1)
+    assert np.array_equal(sc["viewmat"], sc["projmat"]) and sc["viewmat"][2, 3] == 8.0   # w == 1 convention
+    assert sc["cx"] == 160 and sc["cy"] == 100 and abs(sc["fx"] - 160.0) < 1e-9
+    # same seed -> same scene
+    assert np.array_equal(make_scene(5000, 320, 200, scale=0.1, sh_degree=3, seed=3)["means"], sc["means"])
+    cam = rotated_camera(320, 200, 2, n_views=8)
+    R = cam["viewmat"][:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6)
+
+
+def test_flat_layout_matches_pipeline_order():
+    offs, total = parallel.flat_layout(1000, 16)
+    assert total == 1000 * 59
+    names = sorted(offs, key=lambda k: offs[k][0])
+    assert names == ["means", "scales", "quats", "opacities", "coeffs"]   # geometry prefix, SH coefficients last
+    assert offs["coeffs"][0] == 1000 * 11
