@@ -360,7 +360,19 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _watchdog(seconds):
+    """A bench run that stalls (hung kernel / collective) must not block the driver: exit hard after `seconds`."""
+    def fire():
+        sys.stderr.write(f"bench.py watchdog: no result after {seconds}s, aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 if __name__ == "__main__":
+    _watchdog(1500)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
