@@ -43,7 +43,7 @@ def _worker(rank, world, port, ret):
 
 def test_flat_bucket_allreduce_world2():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()   # never fork a multi-threaded pytest process
     ret = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
