@@ -10,6 +10,8 @@ Gradients of all per-Gaussian parameters are written into slices of ONE flat fp3
 (`grad_flat`, 59 floats per Gaussian at SH degree 3) so that data-parallel training needs a single
 NCCL all-reduce per step.
 """
+import os
+
 import torch
 
 from . import capi
@@ -81,6 +83,8 @@ class SplatPipeline:
         self.m = 0
         if m_capacity:
             self._grow(int(m_capacity))
+        self.nvtx = os.environ.get("GSB_NVTX", "0") == "1"
+        self._nvtx_open = False
         self.exchange = None  # multigpu.ViewParallelExchange (fused SH backward + NVLink exchange)
         self.stage_timing = stage_timing
         self.stage_ms = {}
@@ -116,6 +120,12 @@ class SplatPipeline:
 
     # ------------------------------------------------------------------------------------------
     def _stage(self, name):
+        if self.nvtx:   # GSB_NVTX=1: one NVTX range per stage (nsys / ncu --nvtx)
+            if self._nvtx_open:
+                torch.cuda.nvtx.range_pop()
+            self._nvtx_open = not name.startswith("end_")
+            if self._nvtx_open:
+                torch.cuda.nvtx.range_push("gsb:" + name)
         if self.stage_timing:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
