@@ -142,7 +142,7 @@ int gsb_gather_bin_edges(int m, int num_tiles, const int64_t *isect_ids_sorted,
  * gsb_rasterize_forward_packed: the blend kernel alone on an already packed record stream. */
 int gsb_bucket_max_tile_len(void);
 size_t gsb_bucket_cursor_bytes(int num_tiles);
-size_t gsb_bucket_workspace_bytes(int m);
+size_t gsb_bucket_workspace_bytes(int n, int m);
 int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
                            int32_t *tile_bins, int32_t *tile_cursor, int32_t *stats, gsb_stream_t stream);
 int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float *xys, const float *depths,

@@ -109,11 +109,21 @@ __global__ void __launch_bounds__(256)
 bucket_emit_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__ depths,
                    const int *__restrict__ radii, const int *__restrict__ cum_tiles_hit, int tiles_x,
                    int tiles_y, int *__restrict__ cursor, unsigned long long *__restrict__ comp,
-                   int *__restrict__ gaussian_ids) {
+                   int *__restrict__ gaussian_ids, const float *__restrict__ conics,
+                   const float *__restrict__ colors, const float *__restrict__ opacities,
+                   GsbRecord *__restrict__ gattr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int r = radii[i];
     if (r <= 0) return;
+    // the record of this Gaussian is built ONCE here (log2 / sqrt / extents) and only copied per intersection
+    {
+        const GsbRecord rec = make_record(xys[i], __ldg(conics + 3 * i), __ldg(conics + 3 * i + 1),
+                                          __ldg(conics + 3 * i + 2), __ldg(opacities + i), __ldg(colors + 3 * i),
+                                          __ldg(colors + 3 * i + 1), __ldg(colors + 3 * i + 2), 0);
+        float4 *dst = reinterpret_cast<float4 *>(gattr + i);
+        dst[0] = rec.q0; dst[1] = rec.q1; dst[2] = rec.q2;
+    }
     int x0, x1, y0, y1;
     tile_bbox_of(xys[i], r, tiles_x, tiles_y, x0, x1, y0, y1);
     int k = (i == 0) ? 0 : cum_tiles_hit[i - 1];
@@ -247,10 +257,9 @@ __device__ __forceinline__ void cta_radix_sort_depth(u64 *buf, unsigned (*whist)
 template <int MAXI>   // largest items-per-thread instantiation compiled in (register budget): 4, 16 or 64
 __global__ void __launch_bounds__(256)
 tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
-                      const int *__restrict__ gaussian_ids, const float2 *__restrict__ xys,
-                      const float *__restrict__ conics, const float *__restrict__ colors,
-                      const float *__restrict__ opacities, GsbRecord *__restrict__ records,
-                      int *__restrict__ sorted_index, int *__restrict__ gaussian_ids_sorted) {
+                      const int *__restrict__ gaussian_ids, const GsbRecord *__restrict__ gattr,
+                      GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
+                      int *__restrict__ gaussian_ids_sorted) {
     extern __shared__ unsigned long long skey[];
     __shared__ unsigned whist[8][256];
     __shared__ unsigned bin_base[256 + 8];
@@ -338,26 +347,28 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const int k = (int)(unsigned)(skey[i] & 0xffffffffull);
         const int g = gaussian_ids[k];
-        const GsbRecord r = make_record(__ldg(xys + g), __ldg(conics + 3 * g), __ldg(conics + 3 * g + 1),
-                                        __ldg(conics + 3 * g + 2), __ldg(opacities + g), __ldg(colors + 3 * g),
-                                        __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), k);
+        const float4 *src = reinterpret_cast<const float4 *>(gattr + g);   // 3 x 128-bit gather (L2-resident)
+        float4 q0 = __ldg(src);
+        const float4 q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+        q0.w = __int_as_float(k);
         float4 *dst = reinterpret_cast<float4 *>(records + range.x + i);
-        stg_stream4(dst, r.q0);
-        stg_stream4(dst + 1, r.q1);
-        stg_stream4(dst + 2, r.q2);
+        stg_stream4(dst, q0);
+        stg_stream4(dst + 1, q1);
+        stg_stream4(dst + 2, q2);
         if (sorted_index) sorted_index[range.x + i] = k;
         if (gaussian_ids_sorted) gaussian_ids_sorted[range.x + i] = g;
     }
 }
 
 struct BucketLayout {
-    size_t comp, gids, total;
+    size_t comp, gids, gattr, total;
 };
-BucketLayout bucket_layout(int m) {
+BucketLayout bucket_layout(int n, int m) {
     BucketLayout L;
     size_t o = 0;
     L.comp = o; o += gsb_align_up((size_t)m * 8, 256);
     L.gids = o; o += gsb_align_up((size_t)m * 4, 256);
+    L.gattr = o; o += gsb_align_up((size_t)n * sizeof(GsbRecord), 256);
     L.total = o;
     return L;
 }
@@ -372,7 +383,9 @@ extern "C" size_t gsb_bucket_cursor_bytes(int num_tiles) {
     return (size_t)(num_tiles > 0 ? num_tiles : 1) * CUR_STRIDE * sizeof(int);
 }
 
-extern "C" size_t gsb_bucket_workspace_bytes(int m) { return bucket_layout(m > 0 ? m : 0).total + 256; }
+extern "C" size_t gsb_bucket_workspace_bytes(int n, int m) {
+    return bucket_layout(n > 0 ? n : 0, m > 0 ? m : 0).total + 256;
+}
 
 // Phase 1 (before the M read-back): tile sizes -> tile_bins, tile_cursor (gsb_bucket_cursor_bytes(tiles); the
 // padded write cursors for phase 2),
@@ -408,7 +421,7 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
                   opacities && workspace && records);
     GSB_CHECK_ARG(((uintptr_t)workspace % 256) == 0 && ((uintptr_t)records % 16) == 0);
     const int T = tiles_x * tiles_y;
-    const BucketLayout L = bucket_layout(m);
+    const BucketLayout L = bucket_layout(n, m);
     if (workspace_bytes < L.total) {
         gsb_set_error(GSB_ERR_WORKSPACE, "bucket workspace too small", __FILE__, __LINE__);
         return GSB_ERR_WORKSPACE;
@@ -425,8 +438,10 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
     char *ws = (char *)workspace;
     unsigned long long *comp = (unsigned long long *)(ws + L.comp);
     int *gids = (int *)(ws + L.gids);
+    GsbRecord *gattr = (GsbRecord *)(ws + L.gattr);
     bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, reinterpret_cast<const float2 *>(xys), depths, radii,
-                                                         cum_tiles_hit, tiles_x, tiles_y, tile_cursor, comp, gids);
+                                                         cum_tiles_hit, tiles_x, tiles_y, tile_cursor, comp, gids,
+                                                         conics, colors, opacities, gattr);
     const size_t smem = (size_t)cap * 8;
 #define GSB_TSP(MAXI)                                                                                           \
     do {                                                                                                        \
@@ -434,8 +449,8 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
             GSB_CUDA(cudaFuncSetAttribute(tile_sort_pack_kernel<MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                          \
         tile_sort_pack_kernel<MAXI><<<T, 256, smem, s>>>(                                                       \
-            cap, reinterpret_cast<const int2 *>(tile_bins), comp, gids, reinterpret_cast<const float2 *>(xys),   \
-            conics, colors, opacities, reinterpret_cast<GsbRecord *>(records), sorted_index, gaussian_ids_sorted); \
+            cap, reinterpret_cast<const int2 *>(tile_bins), comp, gids, gattr,                                  \
+            reinterpret_cast<GsbRecord *>(records), sorted_index, gaussian_ids_sorted);                         \
     } while (0)
     if (cap <= 1024) GSB_TSP(4);
     else if (cap <= 4096) GSB_TSP(16);

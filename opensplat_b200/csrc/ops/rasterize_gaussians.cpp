@@ -96,7 +96,7 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
     torch::Tensor finalIdx = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kInt32));
     if (maxLen <= gsb_bucket_max_tile_len()) {
         // fast path: two-level bucket sort fused with the record packing
-        const size_t wsBytes = gsb_bucket_workspace_bytes(m);
+        const size_t wsBytes = gsb_bucket_workspace_bytes(n, m);
         torch::Tensor ws = torch::empty({(int64_t)wsBytes + 256}, gsb::like(x, torch::kUInt8));
         char *wp = (char *)ws.data_ptr();
         wp += (256 - ((uintptr_t)wp % 256)) % 256;

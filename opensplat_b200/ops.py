@@ -200,7 +200,7 @@ def bucket_sort_pack(n, m, max_tile_len, xys, depths, radii, cum_tiles_hit, tile
     """Fast-path phase 2: bucket emit + per-tile shared-memory sort + record pack -> records (+ optional
     sorted_index / gaussian_ids_sorted for inspection).  Consumes tile_cursor."""
     L = capi.lib()
-    ws = _ws.get(xys.device, "bucket", L.gsb_bucket_workspace_bytes(m) + 256)
+    ws = _ws.get(xys.device, "bucket", L.gsb_bucket_workspace_bytes(n, m) + 256)
     off = (-ws.data_ptr()) % 256
     records = torch.empty(L.gsb_raster_records_bytes(m), dtype=torch.uint8, device=xys.device)
     idx = _empty((m,), torch.int32, xys) if want_index else None

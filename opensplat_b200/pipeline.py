@@ -103,7 +103,7 @@ class SplatPipeline:
         self.sort_ws = torch.empty(self.L.gsb_sort_workspace_bytes(cap) + 256, dtype=torch.uint8, device=d)
         self.records = torch.empty(self.L.gsb_raster_records_bytes(cap), dtype=torch.uint8, device=d)
         self.grad_rows = torch.empty(self.L.gsb_raster_grad_rows_bytes(cap), dtype=torch.uint8, device=d)
-        self.bucket_ws = torch.empty(self.L.gsb_bucket_workspace_bytes(cap) + 256, dtype=torch.uint8, device=d)
+        self.bucket_ws = torch.empty(self.L.gsb_bucket_workspace_bytes(self.n, cap) + 256, dtype=torch.uint8, device=d)
         self.m_cap = cap
 
     def load_scene(self, sc):

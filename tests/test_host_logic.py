@@ -9,7 +9,7 @@ from opensplat_b200.scene import make_scene, rotated_camera
 def test_workspace_queries_are_monotone_and_aligned():
     L = capi.lib()
     for fn in (L.gsb_sort_workspace_bytes, L.gsb_raster_records_bytes, L.gsb_raster_grad_rows_bytes,
-               L.gsb_bucket_workspace_bytes, L.gsb_cumsum_workspace_bytes):
+               (lambda m: L.gsb_bucket_workspace_bytes(1000, m)), L.gsb_cumsum_workspace_bytes):
         prev = 0
         for m in (0, 1, 100, 2048, 2049, 1_000_000, 50_000_000):
             b = fn(m)
