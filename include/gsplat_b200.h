@@ -213,6 +213,74 @@ int gsb_activate_backward(int n, const float *scales, const float *raw_quats, co
  *   max_2d_size = max(max_2d_size, radii / max(H, W)).  All three are [n] fp32, updated in place. */
 int gsb_densify_stats_update(int n, const float *v_xy, const int32_t *radii, int img_h, int img_w,
                              float *xys_grad_norm, float *vis_counts, float *max_2d_size, gsb_stream_t stream);
+/* gsb_densify_stats_init: the first step after a refinement (model.cpp:321-323,328-330, the `!numel()` branches):
+ *   xys_grad_norm = |v_xy| and vis_counts = 1 for EVERY Gaussian, max_2d_size = 0 then the visible update.
+ *   Overwrites the three buffers (no pre-zeroing). */
+int gsb_densify_stats_init(int n, const float *v_xy, const int32_t *radii, int img_h, int img_w,
+                           float *xys_grad_norm, float *vis_counts, float *max_2d_size, gsb_stream_t stream);
+
+/* ---- Topology edits of Model::afterTrain (model.cpp:339-470) -----------------
+ * The reference's split / duplicate / cull (boolean-mask index + cat + repeat per tensor, and the same again per
+ * Adam state in addToOptimizer :253-279 / removeFromOptimizer :281-308) as one classification + compaction:
+ * gsb_densify_classify decides per parent what survives and writes
+ *     src_map[j] = parent | kind << 30   (j < new_n; kind 0 survivor, 1 / 2 split child of sample 0 / 1, 3 duplicate)
+ *   in the reference's output order cat(originals, split sample 0, split sample 1, dups)[~culls];
+ *   split_rank[i] = rank of parent i among the split parents (-1 if not split): split child `kind` of parent i
+ *   uses row (kind-1) * n_splits + split_rank[i] of the [2*n_splits,3] normal samples (model.cpp:359-360);
+ *   counts (device int32[8]) = {n_splits, kept originals, split parents whose children are kept, kept dups,
+ *   new_n, n_dups, 0, 0} -- the one read-back of a refinement.  src_map needs room for 3n entries (a parent
+ *   yields at most itself + a duplicate, or two split children + a duplicate with itself culled).
+ *   Rules, evaluated as the reference does (fp32, same operation order):
+ *     high  = (xys_grad_norm / vis_counts) * 0.5 * max_dim > densify_grad_thresh             (:343-344)
+ *     split = (max exp(scales) > densify_size_thresh  [|| max_2d_size > split_screen_size if check_split_screen]) && high
+ *     dup   = (max exp(scales) <= densify_size_thresh) && high                                (:375-376)
+ *     cull  = sigmoid(opacity) < cull_alpha_thresh || split-parent ||
+ *             (check_huge && (max exp(scales) > cull_scale_thresh [|| max_2d_size > cull_screen_size if check_cull_screen]))
+ *     children: parent's opacity; split children scales log(exp(s)/size_fac); max_2d_size 0    (:370-372,399-403)
+ *   max_2d_size may be NULL (treated as 0).  workspace: gsb_densify_workspace_bytes(n).
+ * gsb_densify_means_scales builds the new means / scales (split children: mean + R(q/|q|)(exp(s) * sample),
+ *   log(exp(s)/size_fac), :359-373); gsb_densify_gather_rows rebuilds any other [n,row_floats] tensor
+ *   (dst[j,:] = src[parent(j),:]; zero_children = 1 writes zeros for kinds 1-3: the Adam moments of new Gaussians).
+ * gsb_reset_opacity: opacities = min(opacities, max_logit) (:472-475) and, when given, zeroed Adam moments (what
+ *   :477-486 intends; the reference builds the zeroed state and then drops it -- DESIGN.md D14). */
+size_t gsb_densify_workspace_bytes(int n);
+int gsb_densify_classify(int n, const float *scales, const float *opacities, const float *xys_grad_norm,
+                         const float *vis_counts, const float *max_2d_size, float max_dim,
+                         float densify_grad_thresh, float densify_size_thresh, int check_split_screen,
+                         float split_screen_size, float cull_alpha_thresh, int check_huge, float cull_scale_thresh,
+                         int check_cull_screen, float cull_screen_size, float size_fac, void *workspace,
+                         size_t workspace_bytes, int32_t *src_map, int32_t *split_rank, int32_t *counts,
+                         gsb_stream_t stream);
+int gsb_densify_means_scales(int new_n, int n_splits, const int32_t *src_map, const int32_t *split_rank,
+                             const float *samples, const float *means, const float *scales, const float *quats,
+                             float size_fac, float *new_means, float *new_scales, gsb_stream_t stream);
+int gsb_densify_gather_rows(int new_n, int row_floats, const int32_t *src_map, const float *src, float *dst,
+                            int zero_children, gsb_stream_t stream);
+int gsb_reset_opacity(int n, float max_logit, float *opacities, float *exp_avg, float *exp_avg_sq,
+                      gsb_stream_t stream);
+
+/* ---- Scene export (Model::savePly model.cpp:505-558, Model::saveSplat :560-594) ----
+ * Packs the file BODY on the device (the caller writes the text header and copies the rows D2H, typically on a
+ * side stream into pinned memory).  features_dc / features_rest take a row stride in floats so both the reference's
+ * [n,3] + [n,K-1,3] tensors and a merged [n,K,3] block (dc = block, rest = block + 3, strides 3K) are accepted.
+ * keep_crs mirrors Model::keepCrs: means / crs_scale + crs_translation (HOST float[3]), scales log(exp(s)/crs_scale).
+ * gsb_pack_ply_rows: out_rows [n, gsb_ply_row_floats(K)] fp32 = x y z, 0 0 0, f_dc_0..2, f_rest (channel-major,
+ *   "Match Inria's version" :525), opacity, scale_0..2, rot_0..3.  Byte-exact vs the reference when !keep_crs.
+ * gsb_splat_order_keys + gsb_sort_intersects(n, num_tiles = 1, keys, ...) give the reference's row order
+ *   (descending (sum exp(scale)) / (1 + exp(-opacity)), :571-583; ties by ascending index where std::sort is
+ *   unspecified); gsb_pack_splat_rows writes the 32-B rows (mean 3 f32, exp(scale) 3 f32, rgb 3 u8, alpha u8,
+ *   quat 4 u8) in that order (order == NULL: identity). */
+int gsb_ply_row_floats(int sh_bases);
+int gsb_pack_ply_rows(int n, int sh_bases, const float *means, const float *features_dc, int dc_stride,
+                      const float *features_rest, int rest_stride, const float *opacities, const float *scales,
+                      const float *quats, int keep_crs, float crs_scale, const float *crs_translation,
+                      float *out_rows, gsb_stream_t stream);
+int gsb_splat_order_keys(int n, const float *scales, const float *opacities, int keep_crs, float crs_scale,
+                         int64_t *keys, gsb_stream_t stream);
+int gsb_pack_splat_rows(int n, const int32_t *order, const float *means, const float *scales,
+                        const float *features_dc, int dc_stride, const float *opacities, const float *quats,
+                        int keep_crs, float crs_scale, const float *crs_translation, void *out_rows,
+                        gsb_stream_t stream);
 
 /* gsb_ssim_l1_loss: the training loss of Model::mainLoss (model.cpp:780-784): (1-w) * mean|rendered - gt| +
  *   w * (1 - SSIM(rendered, gt)) with the reference's SSIM (ssim.cpp:8-47: 11x11 window gaussian(1.5) evaluated

@@ -25,6 +25,8 @@ SOURCES = {
     "raster_bwd.cu": [],
     "fused.cu": [],
     "ssim.cu": [],
+    "densify.cu": [],
+    "export.cu": ["--fmad=false"],
 }
 
 

@@ -22,6 +22,18 @@ FLAGS = ["-std=c++17", "-O2", "-fPIC", "-DUSE_CUDA", "-D_GLIBCXX_USE_CXX11_ABI=1
 SOURCES = ["project_gaussians.cpp", "rasterize_gaussians.cpp", "spherical_harmonics.cpp", "register.cpp"]
 
 
+def shared_stdcxx_flags():
+    """-L of a directory whose libstdc++.so resolves to the SHARED runtime.  This image's default g++ wrapper has a
+    dangling libstdc++.so symlink and silently falls back to libstdc++.a; a second, statically linked copy of the
+    iostream/locale machinery inside a .so that lives next to libtorch's shared one crashes as soon as a number is
+    formatted (e.g. a TORCH_CHECK message)."""
+    import glob
+    for cand in sorted(glob.glob("/usr/lib/gcc/x86_64-linux-gnu/*/libstdc++.so"), reverse=True):
+        if os.path.exists(cand):   # follows the symlink
+            return ["-L" + os.path.dirname(cand)]
+    return []
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -48,7 +60,7 @@ def build(force=False):
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(cc, SOURCES))
     lib_dir = os.path.join(HERE, "lib")
-    cmd = [CXX, "-shared", "-o", OUT] + objs + [
+    cmd = [CXX, "-shared", "-o", OUT] + objs + shared_stdcxx_flags() + [
         f"-L{lib_dir}", "-lgsplat_b200", "-Wl,-rpath,$ORIGIN", f"-L{TORCH}/lib", f"-Wl,-rpath,{TORCH}/lib",
         "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-L/usr/local/cuda/lib64", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)

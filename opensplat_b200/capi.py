@@ -50,6 +50,17 @@ _SIGS = {
     "gsb_activate_forward": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_activate_backward": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_densify_stats_update": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "gsb_densify_stats_init": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "gsb_densify_workspace_bytes": (_sz, [_i]),
+    "gsb_densify_classify": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _sz,
+                                  _vp, _vp, _vp, _vp]),
+    "gsb_densify_means_scales": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "gsb_densify_gather_rows": (_i, [_i, _i, _vp, _vp, _vp, _i, _vp]),
+    "gsb_reset_opacity": (_i, [_i, _f, _vp, _vp, _vp, _vp]),
+    "gsb_ply_row_floats": (_i, [_i]),
+    "gsb_pack_ply_rows": (_i, [_i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _f, C.POINTER(C.c_float), _vp, _vp]),
+    "gsb_splat_order_keys": (_i, [_i, _vp, _vp, _i, _f, _vp, _vp]),
+    "gsb_pack_splat_rows": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _f, C.POINTER(C.c_float), _vp, _vp]),
     "gsb_ssim_workspace_bytes": (_sz, [_i, _i]),
     "gsb_ssim_l1_loss": (_i, [_i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
     "gsb_adam_step": (_i, [C.c_longlong, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp]),

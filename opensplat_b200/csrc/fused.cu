@@ -128,7 +128,7 @@ activate_backward_kernel(int n, const float *__restrict__ scales, const float *_
 
 // ---- densification statistics of Model::afterTrain (model.cpp:317-337), one pass, no boolean-mask indexing ----
 __global__ void __launch_bounds__(256)
-densify_stats_kernel(int n, const float2 *__restrict__ v_xy, const int *__restrict__ radii, float inv_max_hw,
+densify_stats_kernel(int n, const float2 *__restrict__ v_xy, const int *__restrict__ radii, float max_hw,
                      float *__restrict__ xys_grad_norm, float *__restrict__ vis_counts,
                      float *__restrict__ max_2d_size) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,7 +138,22 @@ densify_stats_kernel(int n, const float2 *__restrict__ v_xy, const int *__restri
     const float2 g = v_xy[i];
     xys_grad_norm[i] += sqrtf(g.x * g.x + g.y * g.y);
     vis_counts[i] += 1.f;
-    max_2d_size[i] = fmaxf(max_2d_size[i], (float)r * inv_max_hw);
+    max_2d_size[i] = fmaxf(max_2d_size[i], (float)r / max_hw);
+}
+
+// first step after a refinement (model.cpp:321-323,328-330): xysGradNorm = |v_xy| and visCounts = 1 for EVERY
+// Gaussian (visible or not), max2DSize = 0 then the visible update
+__global__ void __launch_bounds__(256)
+densify_stats_init_kernel(int n, const float2 *__restrict__ v_xy, const int *__restrict__ radii, float max_hw,
+                          float *__restrict__ xys_grad_norm, float *__restrict__ vis_counts,
+                          float *__restrict__ max_2d_size) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = radii[i];
+    const float2 g = v_xy[i];
+    xys_grad_norm[i] = sqrtf(g.x * g.x + g.y * g.y);
+    vis_counts[i] = 1.f;
+    max_2d_size[i] = r > 0 ? fmaxf(0.f, (float)r / max_hw) : 0.f;
 }
 
 int sm_count() {
@@ -229,9 +244,22 @@ extern "C" int gsb_densify_stats_update(int n, const float *v_xy, const int32_t 
     GSB_CHECK_ARG(n >= 0 && img_h > 0 && img_w > 0);
     if (n == 0) return 0;
     GSB_CHECK_ARG(v_xy && radii && xys_grad_norm && vis_counts && max_2d_size && ((uintptr_t)v_xy % 8) == 0);
-    const float inv = 1.f / (float)(img_h > img_w ? img_h : img_w);
+    const float max_hw = (float)(img_h > img_w ? img_h : img_w);
     densify_stats_kernel<<<gsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        n, reinterpret_cast<const float2 *>(v_xy), radii, inv, xys_grad_norm, vis_counts, max_2d_size);
+        n, reinterpret_cast<const float2 *>(v_xy), radii, max_hw, xys_grad_norm, vis_counts, max_2d_size);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gsb_densify_stats_init(int n, const float *v_xy, const int32_t *radii, int img_h, int img_w,
+                                      float *xys_grad_norm, float *vis_counts, float *max_2d_size,
+                                      gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && img_h > 0 && img_w > 0);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(v_xy && radii && xys_grad_norm && vis_counts && max_2d_size && ((uintptr_t)v_xy % 8) == 0);
+    const float max_hw = (float)(img_h > img_w ? img_h : img_w);
+    densify_stats_init_kernel<<<gsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        n, reinterpret_cast<const float2 *>(v_xy), radii, max_hw, xys_grad_norm, vis_counts, max_2d_size);
     GSB_LAUNCH_CHECK();
     return 0;
 }

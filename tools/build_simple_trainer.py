@@ -25,6 +25,7 @@ def build():
     sys.path.insert(0, ROOT)
     from opensplat_b200 import build_ops
     build_ops.build()
+    shared_stdcxx_flags = build_ops.shared_stdcxx_flags
     tmp = "/tmp/gsb_simple_trainer"
     os.makedirs(tmp, exist_ok=True)
     shutil.copy(REF, os.path.join(tmp, "simple_trainer.cpp"))
@@ -35,7 +36,7 @@ def build():
     cmd = ["g++", "-std=c++17", "-O2", "-DUSE_CUDA", "-D_GLIBCXX_USE_CXX11_ABI=1", "-w",
            f"-I{ops}", f"-I{shims}", f"-I{T}/include", f"-I{T}/include/torch/csrc/api/include",
            "-I/usr/local/cuda/include", os.path.join(tmp, "simple_trainer.cpp"), os.path.join(shims, "cv_utils.cpp"),
-           "-o", OUT, f"-L{lib}", "-lopensplat_b200_ops", "-lgsplat_b200", "-Wl,-rpath,$ORIGIN",
+           "-o", OUT] + shared_stdcxx_flags() + [f"-L{lib}", "-lopensplat_b200_ops", "-lgsplat_b200", "-Wl,-rpath,$ORIGIN",
            f"-L{T}/lib", f"-Wl,-rpath,{T}/lib", "-Wl,--no-as-needed", "-ltorch", "-ltorch_cpu", "-ltorch_cuda",
            "-lc10", "-lc10_cuda", "-L/usr/local/cuda/lib64", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
