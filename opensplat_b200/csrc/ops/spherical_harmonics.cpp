@@ -11,6 +11,12 @@ int degFromSh(int numBases) {
     return 4;
 }
 
+// public helper of the reference's CPU bindings that model.hpp:44 calls (gsplat_cpu.cpp:409-423)
+int numShBases(int degree) {
+    if (degree < 0 || degree > 4) return 25;
+    return (degree + 1) * (degree + 1);
+}
+
 static const double kShC0 = 0.28209479177387814;
 
 torch::Tensor rgb2sh(const torch::Tensor &rgb) { return (rgb - 0.5) / kShC0; }

@@ -82,8 +82,9 @@ class Densifier:
     tensors with leading dimension n; "means", "scales" (log), "quats" (raw), "opacities" (logits, [n,1]) are
     required, anything else (featuresDc / featuresRest / a merged coeffs block) is carried along row-wise."""
 
-    def __init__(self, cfg=None, generator=None, sample_fn=None):
+    def __init__(self, cfg=None, generator=None, sample_fn=None, group=None):
         self.cfg = cfg or RefineConfig()
+        self.group = group
         self.generator = generator
         # sample_fn(rows, device) -> [rows,3] normal samples; default torch.randn on the device (model.cpp:359)
         self.sample_fn = sample_fn
@@ -103,6 +104,20 @@ class Densifier:
         fn = L.gsb_densify_stats_init if first else L.gsb_densify_stats_update
         capi.check(fn(n, capi.ptr(v_xy), capi.ptr(radii), img_h, img_w, capi.ptr(self.xys_grad_norm),
                       capi.ptr(self.vis_counts), capi.ptr(self.max_2d_size), capi.stream()))
+
+    def sync_stats(self, group=None):
+        """Data-parallel replicas render different views, so their statistics differ; reduce them (sum of gradient
+        norms and visibility counts, max of screen sizes) so that every replica classifies identically.  Device
+        agnostic (NCCL on the GPUs, gloo in the CPU tests).  Not in the reference (single GPU); with one rank it is
+        the identity."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+            return
+        if self.xys_grad_norm is None:
+            return
+        dist.all_reduce(self.xys_grad_norm, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.vis_counts, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.max_2d_size, op=dist.ReduceOp.MAX, group=group)
 
     def schedule(self, step):
         """(refine?, densify?, reset_alpha?, check_split_screen, check_huge) for `step` -- model.cpp:339-341,349,441,472."""
@@ -126,6 +141,7 @@ class Densifier:
         if not refine:
             return params, adam_m, adam_v, info
         info["refined"] = True
+        self.sync_stats(self.group)
         if densify:
             params, adam_m, adam_v, r = self.refine(params, adam_m, adam_v, max(img_h, img_w), chk_screen, chk_huge)
             info.update(r)

@@ -25,7 +25,18 @@ class ViewParallelExchange:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         dev = pipe.dev
-        n = pipe.n
+        self._alloc_symmetric(pipe.n)
+        # every rank's camera centre (tiny, exchanged once)
+        cp = torch.as_tensor(cam_pos, dtype=torch.float32, device=dev).reshape(1, 3)
+        allcp = [torch.zeros_like(cp) for _ in range(self.world)]
+        dist.all_gather(allcp, cp, group=self.group)
+        self.cam_positions = torch.cat(allcp, 0).contiguous()
+        self.side = torch.cuda.Stream(device=dev)
+        assert pipe.sizes[-1][0] == "coeffs"
+
+    def _alloc_symmetric(self, n):
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = self.pipe.dev
         # two symmetric buffers (double-buffered so ONE barrier per step is enough, see exchange())
         self.bufs, self.hdls, self.ptrs = [], [], []
         for _ in range(2):
@@ -36,14 +47,14 @@ class ViewParallelExchange:
             self.hdls.append(h)
             self.ptrs.append(h.buffer_ptrs_dev)  # device array of world_size pointers (peer-mapped)
         self.step = 0
-        # every rank's camera centre (tiny, exchanged once)
-        cp = torch.as_tensor(cam_pos, dtype=torch.float32, device=dev).reshape(1, 3)
-        allcp = [torch.zeros_like(cp) for _ in range(self.world)]
-        dist.all_gather(allcp, cp, group=self.group)
-        self.cam_positions = torch.cat(allcp, 0).contiguous()
-        self.side = torch.cuda.Stream(device=dev)
         self.geom_numel = n * 11  # means 3 + scales 3 + quats 4 + opacity 1: the prefix of the flat buffer
-        assert pipe.sizes[-1][0] == "coeffs"
+
+    def resize(self, pipe):
+        """After a refinement changed the Gaussian count (collective: every rank refines in lock-step, see
+        densify.Densifier.sync_stats): new symmetric buffers + rendezvous."""
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+        self._alloc_symmetric(pipe.n)
 
     def v_rgbs_buffer(self):
         """Where this step's rasterize-backward must write its colour gradient."""

@@ -29,7 +29,40 @@ class SplatPipeline:
         self.T = self.tb[0] * self.tb[1]
         self.L = capi.lib()
         d, f32, i32 = self.dev, torch.float32, torch.int32
-        n = self.n
+        self._alloc_gaussians(self.n)
+        # ---- per-pixel ----
+        self.out_img = torch.empty((H, W, 3), dtype=f32, device=d)
+        self.final_Ts = torch.empty((H, W), dtype=f32, device=d)
+        self.final_idx = torch.empty((H, W), dtype=i32, device=d)
+        self.v_img = torch.empty((H, W, 3), dtype=f32, device=d)
+        self.target = torch.zeros((H, W, 3), dtype=f32, device=d)
+        self.background = torch.zeros(3, dtype=f32, device=d)
+        self.loss = torch.zeros(1, dtype=f32, device=d)
+        self.tile_bins = torch.empty((self.T, 2), dtype=i32, device=d)
+        self.tile_cursor = torch.empty(self.L.gsb_bucket_cursor_bytes(self.T), dtype=torch.uint8, device=d)
+        # ---- camera ----
+        self.viewmat = torch.eye(4, dtype=f32, device=d)
+        self.projmat = torch.eye(4, dtype=f32, device=d)
+        self.intr = (1.0, 1.0, 0.0, 0.0)
+        # ---- M-dependent (grown on demand) ----
+        self.m_cap = 0
+        self.m = 0
+        if m_capacity:
+            self._grow(int(m_capacity))
+        self.nvtx = os.environ.get("GSB_NVTX", "0") == "1"
+        self._nvtx_open = False
+        self.exchange = None  # multigpu.ViewParallelExchange (fused SH backward + NVLink exchange)
+        self.stage_timing = stage_timing
+        self.stage_ms = {}
+        self._ev = []
+        self._steps_ev = []
+
+    def _alloc_gaussians(self, n):
+        """(Re)allocates everything sized by the Gaussian count: the flat parameter / gradient buffers with their
+        per-tensor views, Adam state (dropped), and the per-Gaussian intermediates.  Called by __init__ and after a
+        refinement changed the count (resize_gaussians)."""
+        self.n = n = int(n)
+        d, f32, i32 = self.dev, torch.float32, torch.int32
         # ---- parameters: one flat buffer, views per tensor (same layout for grads / Adam state) ----
         self.sizes = [("means", (n, 3)), ("scales", (n, 3)), ("quats", (n, 4)), ("opacities", (n, 1)),
                       ("coeffs", (n, self.K, 3))]
@@ -64,32 +97,7 @@ class SplatPipeline:
         self.total_host = torch.zeros(2, dtype=i32).pin_memory()
         self.max_len = 0
         self._m_event = torch.cuda.Event()
-        # ---- per-pixel ----
-        self.out_img = torch.empty((H, W, 3), dtype=f32, device=d)
-        self.final_Ts = torch.empty((H, W), dtype=f32, device=d)
-        self.final_idx = torch.empty((H, W), dtype=i32, device=d)
-        self.v_img = torch.empty((H, W, 3), dtype=f32, device=d)
-        self.target = torch.zeros((H, W, 3), dtype=f32, device=d)
-        self.background = torch.zeros(3, dtype=f32, device=d)
-        self.loss = torch.zeros(1, dtype=f32, device=d)
-        self.tile_bins = torch.empty((self.T, 2), dtype=i32, device=d)
-        self.tile_cursor = torch.empty(self.L.gsb_bucket_cursor_bytes(self.T), dtype=torch.uint8, device=d)
-        # ---- camera ----
-        self.viewmat = torch.eye(4, dtype=f32, device=d)
-        self.projmat = torch.eye(4, dtype=f32, device=d)
-        self.intr = (1.0, 1.0, 0.0, 0.0)
-        # ---- M-dependent (grown on demand) ----
-        self.m_cap = 0
-        self.m = 0
-        if m_capacity:
-            self._grow(int(m_capacity))
-        self.nvtx = os.environ.get("GSB_NVTX", "0") == "1"
-        self._nvtx_open = False
-        self.exchange = None  # multigpu.ViewParallelExchange (fused SH backward + NVLink exchange)
-        self.stage_timing = stage_timing
-        self.stage_ms = {}
-        self._ev = []
-        self._steps_ev = []
+        self.m_cap = 0   # bucket workspace depends on n: regrown on the next forward
 
     # ------------------------------------------------------------------------------------------
     def _grow(self, m):
@@ -270,6 +278,48 @@ class SplatPipeline:
         self.adam_step(lr=lr)
         self._collect()
         return loss
+
+    # ---- topology edits (Model::afterTrain, model.cpp:311-500) -------------------------------------------
+    def resize_gaussians(self, params, adam_m=None, adam_v=None):
+        """Adopts a new Gaussian set (dicts keyed like self.p; leading dimension = new count): re-allocates the
+        n-sized buffers and copies parameters and Adam moments into the new flat layout."""
+        t = self.adam_t
+        self._alloc_gaussians(params["means"].shape[0])
+        self.adam_t = t
+        for k in self.p:
+            self.p[k].copy_(params[k].view(self.p[k].shape))
+        if adam_m is not None and adam_v is not None:
+            self.adam_m = torch.empty_like(self.param_flat)
+            self.adam_v = torch.empty_like(self.param_flat)
+            o = 0
+            for name, shp in self.sizes:
+                c = int(torch.Size(shp).numel())
+                self.adam_m[o:o + c].copy_(adam_m[name].reshape(-1))
+                self.adam_v[o:o + c].copy_(adam_v[name].reshape(-1))
+                o += c
+        if self.exchange is not None:
+            self.exchange.resize(self)
+
+    def _state_views(self, flat):
+        out, o = {}, 0
+        for name, shp in self.sizes:
+            c = int(torch.Size(shp).numel())
+            out[name] = flat[o:o + c].view(shp)
+            o += c
+        return out
+
+    def after_train(self, densifier, step):
+        """Model::afterTrain for this pipeline: statistics from the last backward pass (self.v_xy, self.radii), and on
+        refine steps split / duplicate / cull / alpha reset of the flat parameter and Adam buffers.  With
+        torch.distributed initialised (data-parallel replicas rendering different views) the statistics are reduced
+        over the ranks before classification so that every replica makes identical edits (give every rank's
+        densifier a generator with the same seed)."""
+        m = self._state_views(self.adam_m) if self.adam_m is not None else None
+        v = self._state_views(self.adam_v) if self.adam_v is not None else None
+        p, m2, v2, info = densifier.after_train(step, dict(self.p), m, v, self.v_xy, self.radii, self.H, self.W)
+        if info.get("n", self.n) != self.n or p["means"].data_ptr() != self.p["means"].data_ptr():
+            self.resize_gaussians(p, m2, v2)
+        return info
 
     # algorithmic HBM bytes of the path for the last step (SURVEY.md 8d / BASELINE.md section 4)
     def algorithmic_bytes(self):

@@ -1,6 +1,6 @@
 """Generates tests/golden/scene_edit_*.npz by running the REFERENCE ITSELF: the unmodified model.cpp
 (Model::afterTrain, Model::save) compiled from /root/reference into oracle/_ref/libopensplat_ref_model.so and
-driven through oracle/ref_model_driver.cpp.  Run in the build container only:
+driven through tests/native/model_driver.cpp.  Run in the build container only:
 
     make -C oracle ref && python tests/golden/make_golden_scene_edit.py
 

@@ -1,8 +1,13 @@
-// oracle/ref_model_driver.cpp -- TEST INFRASTRUCTURE ONLY.
-// Drives the UNMODIFIED reference Model (model.cpp compiled from /root/reference by oracle/Makefile) so that the
-// restatements in oracle/scene_edit.py can be pinned against the reference itself:
-//   torch.ops.opensplat_ref_model.after_train   -> Model::afterTrain  (model.cpp:311-500), incl. the Adam-state surgery
-//   torch.ops.opensplat_ref_model.save          -> Model::save        (model.cpp:496-594; .ply or .splat by extension)
+// tests/native/model_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+// Drives the UNMODIFIED reference Model (model.cpp compiled from /root/reference).  Built twice:
+//  (1) oracle/Makefile -> oracle/_ref/libopensplat_ref_model.so: model.cpp + the reference's own CPU operators; pins the
+//      restatements in oracle/scene_edit.py against the reference itself (torch.ops.opensplat_ref_model.*);
+//  (2) tools/build_model_b200.py -> opensplat_b200/lib/libopensplat_model_b200.so: the SAME unmodified model.cpp compiled
+//      with -DUSE_CUDA against THIS repo's operator layer (csrc/ops) -- the drop-in check that Model::forward /
+//      mainLoss / optimizersStep / afterTrain run unchanged on the B200 back end (torch.ops.opensplat_b200_model.*).
+//   after_train   -> Model::afterTrain  (model.cpp:311-500), incl. the Adam-state surgery
+//   save          -> Model::save        (model.cpp:496-594; .ply or .splat by extension)
+//   train         -> the body of the reference's training loop (opensplat.cpp:151-170) for a few steps
 // Nothing of the reference is copied: a Model is constructed through its own constructor (with a stub for the
 // nanoflann-based PointsTensor::scales(), whose result we overwrite anyway), its public tensors are replaced by the
 // caller's, its optimizers are re-created by its own setupOptimizers(), and the Adam moments are injected as the
@@ -38,7 +43,8 @@ std::pair<Tensor, Tensor> read_state(torch::optim::Adam *opt) {
 std::unique_ptr<Model> make_model(const std::vector<Tensor> &params, int64_t numCameras, int64_t refineEvery,
                                   int64_t warmupLength, int64_t resetAlphaEvery, double densifyGradThresh,
                                   double densifySizeThresh, int64_t stopScreenSizeAt, double splitScreenSize,
-                                  int64_t maxSteps, bool keepCrs, double scale, const Tensor &translation) {
+                                  int64_t maxSteps, bool keepCrs, double scale, const Tensor &translation,
+                                  int64_t shDegreeInterval = 1000) {
     const int64_t n = params[0].size(0);
     const int64_t restBases = params[4].size(1);
     int shDegree = 0;
@@ -48,17 +54,17 @@ std::unique_ptr<Model> make_model(const std::vector<Tensor> &params, int64_t num
     in.translation = translation.clone();
     in.points.xyz = torch::zeros({n, 3}, torch::kFloat32);
     in.points.rgb = torch::zeros({n, 3}, torch::kUInt8);
+    const torch::Device device = params[0].device();
     auto m = std::make_unique<Model>(in, (int)numCameras, /*numDownscales*/ 0, /*resolutionSchedule*/ 3000, shDegree,
-                                     /*shDegreeInterval*/ 1000, (int)refineEvery, (int)warmupLength,
+                                     (int)shDegreeInterval, (int)refineEvery, (int)warmupLength,
                                      (int)resetAlphaEvery, (float)densifyGradThresh, (float)densifySizeThresh,
-                                     (int)stopScreenSizeAt, (float)splitScreenSize, (int)maxSteps, keepCrs,
-                                     torch::Device(torch::kCPU));
-    m->means = params[0].clone().requires_grad_();
-    m->scales = params[1].clone().requires_grad_();
-    m->quats = params[2].clone().requires_grad_();
-    m->featuresDc = params[3].clone().requires_grad_();
-    m->featuresRest = params[4].clone().requires_grad_();
-    m->opacities = params[5].clone().requires_grad_();
+                                     (int)stopScreenSizeAt, (float)splitScreenSize, (int)maxSteps, keepCrs, device);
+    m->means = params[0].detach().clone().requires_grad_();
+    m->scales = params[1].detach().clone().requires_grad_();
+    m->quats = params[2].detach().clone().requires_grad_();
+    m->featuresDc = params[3].detach().clone().requires_grad_();
+    m->featuresRest = params[4].detach().clone().requires_grad_();
+    m->opacities = params[5].detach().clone().requires_grad_();
     m->releaseOptimizers();
     m->setupOptimizers();
     return m;
@@ -117,9 +123,55 @@ void save(std::vector<Tensor> params, std::string filename, int64_t step, bool k
     m->save(filename, (int)step);
 }
 
+// The body of the reference's training loop (opensplat.cpp:151-170) for steps first_step .. first_step+num_steps-1,
+// cameras taken round-robin: zero_grad -> Model::forward -> Model::mainLoss -> backward -> optimizersStep ->
+// schedulersStep -> afterTrain.  Returns {losses [S], gaussian counts [S], last rendered image, params(6)}.
+std::vector<Tensor> train(std::vector<Tensor> params, Tensor camToWorlds, Tensor gts, double fx, double fy, double cx,
+                          double cy, int64_t height, int64_t width, int64_t first_step, int64_t num_steps,
+                          double ssimWeight, int64_t seed, int64_t shDegreeInterval, int64_t numCameras,
+                          int64_t refineEvery, int64_t warmupLength, int64_t resetAlphaEvery, double densifyGradThresh,
+                          double densifySizeThresh, int64_t stopScreenSizeAt, double splitScreenSize, int64_t maxSteps) {
+    auto m = make_model(params, numCameras, refineEvery, warmupLength, resetAlphaEvery, densifyGradThresh,
+                        densifySizeThresh, stopScreenSizeAt, splitScreenSize, maxSteps, false, 1.0,
+                        torch::zeros({3}, torch::kFloat32), shDegreeInterval);
+    const torch::Device device = params[0].device();
+    const int64_t V = camToWorlds.size(0);
+    std::vector<Camera> cams;
+    for (int64_t v = 0; v < V; ++v)
+        cams.emplace_back((int)width, (int)height, (float)fx, (float)fy, (float)cx, (float)cy, 0.f, 0.f, 0.f, 0.f, 0.f,
+                          camToWorlds[v].to(torch::kCPU).clone(), "");
+    torch::manual_seed((uint64_t)seed);
+    std::vector<float> losses;
+    std::vector<int64_t> counts;
+    Tensor rgb;
+    for (int64_t step = first_step; step < first_step + num_steps; ++step) {
+        const int64_t v = (step - 1) % V;
+        m->optimizersZeroGrad();
+        rgb = m->forward(cams[v], (int)step);
+        Tensor gt = gts[v].to(device);
+        Tensor loss = m->mainLoss(rgb, gt, (float)ssimWeight);
+        loss.backward();
+        losses.push_back(loss.item<float>());
+        m->optimizersStep();
+        m->schedulersStep((int)step);
+        m->afterTrain((int)step);
+        counts.push_back(m->means.size(0));
+    }
+    std::vector<Tensor> out = {torch::tensor(losses), torch::tensor(counts), rgb.detach().clone(),
+                               m->means.detach().clone(),      m->scales.detach().clone(),
+                               m->quats.detach().clone(),      m->featuresDc.detach().clone(),
+                               m->featuresRest.detach().clone(), m->opacities.detach().clone()};
+    return out;
+}
+
 }  // namespace
 
-TORCH_LIBRARY(opensplat_ref_model, m) {
+#ifndef GSB_DRIVER_LIB
+#define GSB_DRIVER_LIB opensplat_ref_model
+#endif
+
+TORCH_LIBRARY(GSB_DRIVER_LIB, m) {
     m.def("after_train", &after_train);
     m.def("save", &save);
+    m.def("train", &train);
 }

@@ -56,3 +56,35 @@ def test_view_sharding_covers_all_views_once():
     for world in (1, 2, 4, 8):
         seen = sorted(v for r in range(world) for v in parallel.views_for_rank(8, r, world))
         assert seen == list(range(8))
+
+
+def _stats_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from opensplat_b200.densify import Densifier
+    dn = Densifier()
+    n = 1000
+    g = torch.Generator().manual_seed(100 + rank)     # every rank saw different views
+    dn.xys_grad_norm = torch.rand(n, generator=g)
+    dn.vis_counts = torch.randint(1, 5, (n,), generator=g).float()
+    dn.max_2d_size = torch.rand(n, generator=g)
+    mine = (dn.xys_grad_norm.clone(), dn.vis_counts.clone(), dn.max_2d_size.clone())
+    dn.sync_stats()
+    ret[rank] = tuple(t.numpy() for t in mine) + tuple(t.numpy() for t in (dn.xys_grad_norm, dn.vis_counts, dn.max_2d_size))
+    dist.destroy_process_group()
+
+
+def test_densify_stats_sync_world2():
+    """Replicas must classify identically: statistics are summed / maxed over the ranks before a refinement."""
+    import numpy as np
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_stats_worker, args=(world, port, ret), nprocs=world, join=True)
+    a, b = ret[0], ret[1]
+    for r in (a, b):
+        assert np.array_equal(r[3], a[0] + b[0]) and np.array_equal(r[4], a[1] + b[1])
+        assert np.array_equal(r[5], np.maximum(a[2], b[2]))
+    assert all(np.array_equal(a[i], b[i]) for i in (3, 4, 5))       # identical on every rank

@@ -45,3 +45,21 @@ def test_flat_layout_matches_pipeline_order():
     names = sorted(offs, key=lambda k: offs[k][0])
     assert names == ["means", "scales", "quats", "opacities", "coeffs"]   # geometry prefix, SH coefficients last
     assert offs["coeffs"][0] == 1000 * 11
+
+
+def test_refine_schedule_matches_reference_defaults():
+    """Model::afterTrain's step arithmetic (model.cpp:339-341,349,441,472) with the CLI defaults (opensplat.cpp:30-43):
+    refine every 100 steps after 500, reset interval 3000, densify unless within numCameras+100 steps after a reset
+    boundary, stop splitting at 15000, screen-size rules until 4000, huge cull after 3000."""
+    from opensplat_b200.densify import Densifier, RefineConfig
+    dn = Densifier(RefineConfig(num_cameras=50))
+    sch = dn.schedule
+    assert sch(499)[0] is False and sch(500)[0] is False and sch(550)[0] is False
+    assert sch(600)[:3] == (True, True, False)                   # 600 % 3000 = 600 > 150
+    assert sch(3000)[:3] == (True, False, False)                 # 0 > 150 is false: no densification on the boundary
+    assert sch(3100)[:3] == (True, False, True)                  # alpha reset at boundary + refineEvery
+    assert sch(3200)[:3] == (True, True, False)
+    assert sch(3900)[3] is True and sch(4000)[3] is False        # screen-size rules
+    assert sch(3000)[4] is False and sch(3100)[4] is True        # huge cull only after refineEvery * resetAlphaEvery
+    assert sch(15000)[:3] == (True, False, False) and sch(14900)[1] is True
+    assert RefineConfig(max_steps=30001).stop_split_at == 15000
