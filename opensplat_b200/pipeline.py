@@ -279,7 +279,7 @@ class SplatPipeline:
         self._collect()
         return loss
 
-    # ---- topology edits (Model::afterTrain, model.cpp:311-500) -------------------------------------------
+    # ---- changing the Gaussian count (after topology edits, densify.Densifier / model.GaussianModel) ------------
     def resize_gaussians(self, params, adam_m=None, adam_v=None):
         """Adopts a new Gaussian set (dicts keyed like self.p; leading dimension = new count): re-allocates the
         n-sized buffers and copies parameters and Adam moments into the new flat layout."""
@@ -299,27 +299,6 @@ class SplatPipeline:
                 o += c
         if self.exchange is not None:
             self.exchange.resize(self)
-
-    def _state_views(self, flat):
-        out, o = {}, 0
-        for name, shp in self.sizes:
-            c = int(torch.Size(shp).numel())
-            out[name] = flat[o:o + c].view(shp)
-            o += c
-        return out
-
-    def after_train(self, densifier, step):
-        """Model::afterTrain for this pipeline: statistics from the last backward pass (self.v_xy, self.radii), and on
-        refine steps split / duplicate / cull / alpha reset of the flat parameter and Adam buffers.  With
-        torch.distributed initialised (data-parallel replicas rendering different views) the statistics are reduced
-        over the ranks before classification so that every replica makes identical edits (give every rank's
-        densifier a generator with the same seed)."""
-        m = self._state_views(self.adam_m) if self.adam_m is not None else None
-        v = self._state_views(self.adam_v) if self.adam_v is not None else None
-        p, m2, v2, info = densifier.after_train(step, dict(self.p), m, v, self.v_xy, self.radii, self.H, self.W)
-        if info.get("n", self.n) != self.n or p["means"].data_ptr() != self.p["means"].data_ptr():
-            self.resize_gaussians(p, m2, v2)
-        return info
 
     # algorithmic HBM bytes of the path for the last step (SURVEY.md 8d / BASELINE.md section 4)
     def algorithmic_bytes(self):

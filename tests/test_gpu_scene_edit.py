@@ -257,3 +257,35 @@ def test_export_throughput_smoke():
     assert torch.equal(rows[:, 9:54].reshape(n, 3, 15), p["coeffs"][:, 1:].transpose(1, 2))
     s = export.pack_splat_rows(p)
     assert s.shape == (n, 32)
+
+
+def test_pipeline_resize_gaussians_keeps_rendering():
+    """SplatPipeline.resize_gaussians: adopt a compacted / grown Gaussian set (new flat layout, Adam moments carried
+    over, n-sized intermediates re-allocated) and keep stepping."""
+    from opensplat_b200.pipeline import SplatPipeline
+    from opensplat_b200.scene import make_scene
+    n, W, H = 20_000, 320, 240
+    sc = make_scene(n, W, H, scale=0.05, sh_degree=3, seed=3)
+    pipe = SplatPipeline(n, W, H, device=DEV)
+    pipe.load_scene(sc)
+    pipe.target.copy_(torch.rand(H, W, 3, device=DEV))
+    l0 = float(pipe.train_step())
+    keep = torch.arange(0, n, 2, device=DEV)                         # drop every other Gaussian, then duplicate 100
+    idx = torch.cat([keep, keep[:100]])
+    views = lambda flat: {name: flat[o:o + c].view(shp) for (name, shp), (o, c) in zip(
+        pipe.sizes, [(sum(int(torch.Size(s).numel()) for _, s in pipe.sizes[:i]), int(torch.Size(pipe.sizes[i][1]).numel()))
+                     for i in range(len(pipe.sizes))])}
+    newp = {k: v[idx].clone() for k, v in pipe.p.items()}
+    newm = {k: v[idx].clone() for k, v in views(pipe.adam_m).items()}
+    newv = {k: v[idx].clone() for k, v in views(pipe.adam_v).items()}
+    vd = pipe.viewdirs[idx].clone()
+    t = pipe.adam_t
+    pipe.resize_gaussians(newp, newm, newv)
+    pipe.viewdirs.copy_(vd)
+    assert pipe.n == idx.numel() and pipe.adam_t == t and pipe.param_flat.numel() == pipe.n * 59
+    for k in newp:
+        assert torch.equal(pipe.p[k], newp[k])
+    assert torch.equal(pipe.adam_m[:pipe.n * 3].view(-1, 3), newm["means"])
+    l1 = float(pipe.train_step())
+    l2 = float(pipe.train_step())
+    assert np.isfinite([l0, l1, l2]).all() and pipe.m > 0
