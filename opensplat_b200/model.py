@@ -133,7 +133,7 @@ class GaussianModel:
         tb = ops.tile_bounds(width, height)
         xys, depths, radii, conics, num_tiles_hit, _ = ops.ProjectGaussians.apply(
             self.means, scales, 1.0, quats, view, proj @ view, fx, fy, cx, cy, height, width, tb)
-        self.xys, self.radii = xys, radii
+        self.xys, self.radii, self.numTilesHit = xys, radii, num_tiles_hit
         xys.retain_grad()
         if float(radii.sum()) == 0.0:
             return self.backgroundColor.repeat(height, width, 1)

@@ -25,7 +25,14 @@ def model_scene(n, W, H, seed=0):
     from opensplat_b200.scene import make_scene
     sc = make_scene(n, W, H, scale=0.02, sh_degree=3, opacity=(0.05, 0.6), seed=seed)
     f = np.float32
-    p = {"means": sc["means"], "scales": np.log(sc["scales"]).astype(f), "quats": sc["quats"],
+    # make_scene lays the Gaussians out for simple_trainer's w == 1 projection (x, y in [-1,1] ARE the NDC
+    # coordinates).  Model::forward uses a true perspective P*V (ndc = (2 fx / W) x / z), so scale x, y by the view
+    # depth to land every Gaussian on the same pixel with the same footprint (same M, same tile lists as C2).
+    means = sc["means"].copy()
+    z = means[:, 2] + 8.0
+    means[:, 0] *= z * (W / (2.0 * sc["fx"]))
+    means[:, 1] *= z * (H / (2.0 * sc["fy"]))
+    p = {"means": means.astype(f), "scales": np.log(sc["scales"]).astype(f), "quats": sc["quats"],
          "featuresDc": np.ascontiguousarray(sc["coeffs"][:, 0, :]),
          "featuresRest": np.ascontiguousarray(sc["coeffs"][:, 1:, :]),
          "opacities": np.log(sc["opacities"] / (1 - sc["opacities"])).astype(f)}
@@ -52,6 +59,11 @@ def main():
     gts = torch.rand(1, H, W, 3)
     cfg = RefineConfig(warmup_length=10 ** 6)            # statistics every step, no refinement inside the timed loop
     out = {"workload": f"model_train_{a.n}_{W}x{H}_sh3", "steps": a.steps}
+    probe = GaussianModel({k: torch.from_numpy(v) for k, v in p.items()}, cfg, device=dev)
+    probe.forward(Camera(W, H, fx, fy, cx, cy, c2w[0]), 3001)
+    out["visible"] = int((probe.radii > 0).sum())
+    out["M"] = int(probe.numTilesHit.sum())
+    del probe
 
     def run_cpp(first, steps):
         params = [torch.from_numpy(p[x]).to(dev) for x in PARAM_NAMES]
@@ -90,7 +102,7 @@ def main():
     t0 = time.perf_counter()
     for s in range(3006, 3006 + a.steps):
         loss = step_py(s)
-    lv = float(loss)
+    lv = float(loss.detach())
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / a.steps
     out["gaussian_model_fused_glue"] = {"iters_per_s": 1.0 / dt, "ms_per_iter": dt * 1e3, "final_loss": lv}
