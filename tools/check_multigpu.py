@@ -50,10 +50,39 @@ ok = err_geo == 0.0 and rel_sh < 1e-5
 for _ in range(3):
     b.train_step(world_size=world)
 sync = parallel.replicas_in_sync(b.param_flat, world)
+# a refinement changes the Gaussian count on every replica in lock-step (densify.Densifier.sync_stats makes the
+# decisions identical): new flat layout + new symmetric buffers, and the fused exchange keeps matching plain NCCL
+keep = torch.arange(0, n, 2, device=dev)
+idx = torch.cat([keep, keep[:1000]])
+o, views_m, views_v = 0, {}, {}
+for name, shp in b.sizes:
+    c = int(torch.Size(shp).numel())
+    views_m[name], views_v[name] = b.adam_m[o:o + c].view(shp), b.adam_v[o:o + c].view(shp)
+    o += c
+newp = {k: v[idx].clone() for k, v in b.p.items()}
+newm = {k: v[idx].clone() for k, v in views_m.items()}
+newv = {k: v[idx].clone() for k, v in views_v.items()}
+vd_new = b.viewdirs[idx].clone()
+b.resize_gaussians(newp, newm, newv)
+b.viewdirs.copy_(vd_new)
+for _ in range(2):
+    b.forward(); b.backward()
+c = SplatPipeline(b.n, W, H, device=dev)
+c.set_camera(cam)
+c.param_flat.copy_(b.param_flat); c.viewdirs.copy_(b.viewdirs); c.target.copy_(b.target)
+c.forward(); c.backward()
+parallel.allreduce_gradients(c.grad_flat, world, average=True)
+torch.cuda.synchronize()
+geo2 = b.n * 11
+ok2 = float((c.grad_flat[:geo2] - b.grad_flat[:geo2]).abs().max()) == 0.0 and \
+    float((c.grad_flat[geo2:] - b.grad_flat[geo2:]).norm() / c.grad_flat[geo2:].norm()) < 1e-5
+b.train_step(world_size=world)
+sync = sync and parallel.replicas_in_sync(b.param_flat, world)
+ok = ok and ok2
 res = torch.tensor([int(ok), int(sync)], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"multigpu check world={world}: geometry max|d|={err_geo:.3g} sh rel-L2={rel_sh:.3g} "
+    print(f"multigpu check world={world}: geometry max|d|={err_geo:.3g} sh rel-L2={rel_sh:.3g} after_resize_ok={ok2} "
           f"fused_ok={bool(res[0])} replicas_in_sync={bool(res[1])}")
 dist.destroy_process_group()
 sys.exit(0 if bool(res[0]) and bool(res[1]) else 1)
