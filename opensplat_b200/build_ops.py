@@ -19,7 +19,8 @@ CXX = os.environ.get("CXX", "g++")
 FLAGS = ["-std=c++17", "-O2", "-fPIC", "-DUSE_CUDA", "-D_GLIBCXX_USE_CXX11_ABI=1", "-w",
          f"-I{TORCH}/include", f"-I{TORCH}/include/torch/csrc/api/include", "-I/usr/local/cuda/include",
          f"-I{SRC}"]
-SOURCES = ["project_gaussians.cpp", "rasterize_gaussians.cpp", "spherical_harmonics.cpp", "register.cpp"]
+SOURCES = ["project_gaussians.cpp", "rasterize_gaussians.cpp", "spherical_harmonics.cpp", "fused_extras.cpp",
+           "register.cpp"]
 
 
 def shared_stdcxx_flags():

@@ -5,6 +5,7 @@
 #include "project_gaussians.hpp"
 #include "rasterize_gaussians.hpp"
 #include "spherical_harmonics.hpp"
+#include "fused_extras.hpp"
 
 static std::vector<torch::Tensor> op_project(torch::Tensor means, torch::Tensor scales, double globScale,
                                              torch::Tensor quats, torch::Tensor viewMat, torch::Tensor projMat,
@@ -35,9 +36,28 @@ static std::vector<torch::Tensor> op_bin_and_sort(int64_t numPoints, int64_t num
     return {std::get<0>(t), std::get<1>(t), std::get<2>(t), std::get<3>(t), std::get<4>(t)};
 }
 
+static torch::Tensor op_main_loss(torch::Tensor rgb, torch::Tensor gt, double ssimWeight) {
+    return gsb::MainLoss::apply(rgb, gt, ssimWeight);
+}
+
+static void op_adam_step(torch::Tensor param, torch::Tensor grad, torch::Tensor expAvg, torch::Tensor expAvgSq,
+                         double lr, int64_t step, double beta1, double beta2, double eps) {
+    gsb::adamStep(param, grad, expAvg, expAvgSq, lr, step, beta1, beta2, eps);
+}
+
+static void op_densify_stats(torch::Tensor xysGrad, torch::Tensor radii, int64_t imgHeight, int64_t imgWidth,
+                             bool first, torch::Tensor xysGradNorm, torch::Tensor visCounts, torch::Tensor max2DSize) {
+    gsb::densifyStats(xysGrad, radii, (int)imgHeight, (int)imgWidth, first, xysGradNorm, visCounts, max2DSize);
+}
+
 TORCH_LIBRARY(opensplat_b200, m) {
     m.def("project_gaussians", &op_project);
     m.def("rasterize_gaussians", &op_rasterize);
     m.def("spherical_harmonics", &op_sh);
     m.def("bin_and_sort_gaussians", &op_bin_and_sort);
+    m.def("main_loss", &op_main_loss);
+    m.def("adam_step_(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, int step, "
+          "float beta1, float beta2, float eps) -> ()", &op_adam_step);
+    m.def("densify_stats_(Tensor xys_grad, Tensor radii, int img_height, int img_width, bool first, "
+          "Tensor(a!) xys_grad_norm, Tensor(b!) vis_counts, Tensor(c!) max_2d_size) -> ()", &op_densify_stats);
 }

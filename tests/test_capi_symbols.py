@@ -47,3 +47,25 @@ def test_cubin_is_sm100a_and_uses_tma_bulk_copy():
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "UBLKCP" in out  # cp.async.bulk in the blend kernels
+
+
+def test_cxx_libraries_use_the_shared_libstdcxx():
+    """A C++ .so that carries its own statically linked copy of libstdc++'s iostream / locale code next to the
+    shared one libtorch uses crashes as soon as it formats a number on a stream created by the other copy (seen
+    here: the image's default g++ wrapper has a dangling libstdc++.so symlink and silently falls back to
+    libstdc++.a).  build_ops.shared_stdcxx_flags() / oracle/Makefile STDCXX_DIR prevent it; this pins it."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libs = [os.path.join(root, "opensplat_b200", "lib", "libopensplat_b200_ops.so"),
+            os.path.join(root, "opensplat_b200", "lib", "libopensplat_model_b200.so"),
+            os.path.join(root, "oracle", "_ref", "libopensplat_ref_cpu.so"),
+            os.path.join(root, "oracle", "_ref", "libopensplat_ref_model.so")]
+    checked = 0
+    for lib in libs:
+        if not os.path.exists(lib):
+            continue
+        out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+        assert "_ZNSo9_M_insertIlEERSoT_" not in out, f"{lib} embeds a static copy of libstdc++ (ostream::_M_insert<long>)"
+        checked += 1
+    assert checked >= 1

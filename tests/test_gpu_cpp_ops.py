@@ -122,3 +122,52 @@ def test_reference_simple_trainer_unchanged_runs_on_b200_backend():
     py = _python_simple_trainer(W, H, n, iters)
     assert abs(py[0] - losses[0]) <= 1e-5 * max(1.0, abs(py[0]))   # same forward on the same seeded scene
     assert np.abs(np.array(py) - np.array(losses)).max() <= 2e-3 * max(py)  # same trajectory
+
+
+# ---- optional fused replacements for the ATen glue in Model (csrc/ops/fused_extras.hpp) ----------------------
+def test_cpp_main_loss_vs_reference_golden():
+    o = cpp_ops.ops()
+    g = load_golden("loss_45x70")
+    dev = "cuda:0"
+    rend = torch.from_numpy(g["rendered"]).to(dev).requires_grad_()
+    loss = o.main_loss(rend, torch.from_numpy(g["gt"]).to(dev), float(g["ssim_weight"]))
+    (2.0 * loss).backward()
+    assert abs(float(loss.detach()) - float(g["ref_loss"])) <= 2e-6                  # vs the reference's Model::mainLoss
+    assert rel_l2(rend.grad.cpu().numpy(), 2.0 * g["ref_v_rendered"]) <= 2e-5
+    r2 = torch.from_numpy(g["rendered"]).to(dev).requires_grad_()
+    l2 = ops.MainLoss.apply(r2, torch.from_numpy(g["gt"]).to(dev), float(g["ssim_weight"]))
+    l2.backward()
+    assert float(l2.detach()) == float(loss.detach()) and torch.equal(2.0 * r2.grad, rend.grad)   # same kernels
+
+
+def test_cpp_adam_step_matches_torch_adam():
+    o = cpp_ops.ops()
+    torch.manual_seed(3)
+    p = torch.randn(100_003, device="cuda:0")
+    q = p.clone().requires_grad_()
+    opt = torch.optim.Adam([q], lr=0.005)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 5):
+        g = torch.randn_like(p) * 0.1
+        q.grad = g.clone()
+        opt.step()
+        o.adam_step_(p, g, m, v, 0.005, step, 0.9, 0.999, 1e-8)
+        assert float((p - q.detach()).abs().max()) <= 2e-6
+    st = opt.state[q]
+    assert float((m - st["exp_avg"]).abs().max()) <= 1e-7 and float((v - st["exp_avg_sq"]).abs().max()) <= 1e-8
+
+
+def test_cpp_densify_stats_matches_python_path():
+    from opensplat_b200.densify import Densifier
+    o = cpp_ops.ops()
+    dev = "cuda:0"
+    torch.manual_seed(4)
+    n, H, W = 50_000, 300, 480
+    dn = Densifier()
+    gn, vc, ms = (torch.empty(n, device=dev) for _ in range(3))
+    for i in range(3):
+        v_xy = torch.randn(n, 2, device=dev) * 1e-4
+        radii = torch.randint(-5, 60, (n,), device=dev, dtype=torch.int32)
+        dn.accumulate(v_xy, radii, H, W)
+        o.densify_stats_(v_xy, radii, H, W, i == 0, gn, vc, ms)
+    assert torch.equal(gn, dn.xys_grad_norm) and torch.equal(vc, dn.vis_counts) and torch.equal(ms, dn.max_2d_size)
