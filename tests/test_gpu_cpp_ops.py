@@ -137,7 +137,9 @@ def test_cpp_main_loss_vs_reference_golden():
     r2 = torch.from_numpy(g["rendered"]).to(dev).requires_grad_()
     l2 = ops.MainLoss.apply(r2, torch.from_numpy(g["gt"]).to(dev), float(g["ssim_weight"]))
     l2.backward()
-    assert float(l2.detach()) == float(loss.detach()) and torch.equal(2.0 * r2.grad, rend.grad)   # same kernels
+    # same kernels behind both layers; the scalar is an atomic float sum (last-bit order dependence)
+    assert abs(float(l2.detach()) - float(loss.detach())) <= 1e-7
+    assert float((2.0 * r2.grad - rend.grad).abs().max()) <= 1e-9
 
 
 def test_cpp_adam_step_matches_torch_adam():
