@@ -237,7 +237,7 @@ int gsb_densify_stats_init(int n, const float *v_xy, const int32_t *radii, int i
  *     cull  = sigmoid(opacity) < cull_alpha_thresh || split-parent ||
  *             (check_huge && (max exp(scales) > cull_scale_thresh [|| max_2d_size > cull_screen_size if check_cull_screen]))
  *     children: parent's opacity; split children scales log(exp(s)/size_fac); max_2d_size 0    (:370-372,399-403)
- *   max_2d_size may be NULL (treated as 0).  workspace: gsb_densify_workspace_bytes(n).
+ *   max_2d_size may be NULL (treated as 0).  workspace: gsb_densify_workspace_bytes(n).  n < 2^29.
  * gsb_densify_means_scales builds the new means / scales (split children: mean + R(q/|q|)(exp(s) * sample),
  *   log(exp(s)/size_fac), :359-373); gsb_densify_gather_rows rebuilds any other [n,row_floats] tensor
  *   (dst[j,:] = src[parent(j),:]; zero_children = 1 writes zeros for kinds 1-3: the Adam moments of new Gaussians).

@@ -269,7 +269,7 @@ extern "C" int gsb_densify_classify(int n, const float *scales, const float *opa
                                     float cull_scale_thresh, int check_cull_screen, float cull_screen_size,
                                     float size_fac, void *workspace, size_t workspace_bytes, int32_t *src_map,
                                     int32_t *split_rank, int32_t *counts, gsb_stream_t stream) {
-    GSB_CHECK_ARG(n >= 0 && n < (1 << KIND_SHIFT));
+    GSB_CHECK_ARG(n >= 0 && n < (1 << (KIND_SHIFT - 1)));  // parent in 30 bits, new_n <= 3n in an int32
     GSB_CHECK_ARG(counts != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) {
