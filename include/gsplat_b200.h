@@ -275,6 +275,13 @@ int gsb_pack_ply_rows(int n, int sh_bases, const float *means, const float *feat
                       const float *features_rest, int rest_stride, const float *opacities, const float *scales,
                       const float *quats, int keep_crs, float crs_scale, const float *crs_translation,
                       float *out_rows, gsb_stream_t stream);
+/* gsb_unpack_ply_rows: the inverse (Model::loadPly's per-row reads + reshape/transpose, model.cpp:724-746): PLY
+ *   vertex rows -> the six parameter tensors; with keep_crs, means = (means - translation) * scale and
+ *   scales = log(scale * exp(scales)) (model.cpp:737-740).  Normals are ignored. */
+int gsb_unpack_ply_rows(int n, int sh_bases, const float *rows, int keep_crs, float crs_scale,
+                        const float *crs_translation, float *means, float *features_dc, int dc_stride,
+                        float *features_rest, int rest_stride, float *opacities, float *scales, float *quats,
+                        gsb_stream_t stream);
 int gsb_splat_order_keys(int n, const float *scales, const float *opacities, int keep_crs, float crs_scale,
                          int64_t *keys, gsb_stream_t stream);
 int gsb_pack_splat_rows(int n, const int32_t *order, const float *means, const float *scales,

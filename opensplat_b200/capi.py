@@ -59,6 +59,7 @@ _SIGS = {
     "gsb_reset_opacity": (_i, [_i, _f, _vp, _vp, _vp, _vp]),
     "gsb_ply_row_floats": (_i, [_i]),
     "gsb_pack_ply_rows": (_i, [_i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _f, C.POINTER(C.c_float), _vp, _vp]),
+    "gsb_unpack_ply_rows": (_i, [_i, _i, _vp, _i, _f, C.POINTER(C.c_float), _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "gsb_splat_order_keys": (_i, [_i, _vp, _vp, _i, _f, _vp, _vp]),
     "gsb_pack_splat_rows": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _f, C.POINTER(C.c_float), _vp, _vp]),
     "gsb_ssim_workspace_bytes": (_sz, [_i, _i]),

@@ -54,6 +54,37 @@ pack_ply_kernel(long long total, int rf, int k, const float *__restrict__ means,
     }
 }
 
+// inverse of pack_ply_kernel (Model::loadPly, model.cpp:724-746): rows -> the six parameter tensors; keepCrs applies
+// means = (means - translation) * scale, scales = log(scale * exp(scales)).
+__global__ void __launch_bounds__(256)
+unpack_ply_kernel(long long total, int rf, int k, const float *__restrict__ rows, Crs crs, float *__restrict__ means,
+                  float *__restrict__ dc, int dc_stride, float *__restrict__ rest, int rest_stride,
+                  float *__restrict__ opac, float *__restrict__ scales, float *__restrict__ quats) {
+    const int nrest = 3 * (k - 1);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx / rf;
+        int c = (int)(idx - i * rf);
+        float v = rows[idx];
+        if (c < 3) {
+            if (crs.keep) v = (v - (c == 0 ? crs.tx : c == 1 ? crs.ty : crs.tz)) * crs.scale;
+            means[3 * i + c] = v;
+        } else if (c < 6) {
+            // normals: ignored
+        } else if (c < 9) {
+            dc[i * dc_stride + (c - 6)] = v;
+        } else if (c < 9 + nrest) {
+            const int r = c - 9, ch = r / (k - 1), b = r - ch * (k - 1);
+            rest[i * rest_stride + 3 * b + ch] = v;
+        } else {
+            c -= 9 + nrest;
+            if (c == 0) opac[i] = v;
+            else if (c < 4) scales[3 * i + (c - 1)] = crs.keep ? logf(crs.scale * expf(v)) : v;
+            else quats[4 * i + (c - 4)] = v;
+        }
+    }
+}
+
 __device__ __forceinline__ float splat_alpha_den(float o) { return 1.f + expf(-o); }
 
 __global__ void __launch_bounds__(256)
@@ -132,6 +163,25 @@ extern "C" int gsb_pack_ply_rows(int n, int sh_bases, const float *means, const 
     pack_ply_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         total, rf, sh_bases, means, features_dc, dc_stride, features_rest, rest_stride, opacities, scales, quats,
         make_crs(keep_crs, crs_scale, crs_translation), out_rows);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gsb_unpack_ply_rows(int n, int sh_bases, const float *rows, int keep_crs, float crs_scale,
+                                   const float *crs_translation, float *means, float *features_dc, int dc_stride,
+                                   float *features_rest, int rest_stride, float *opacities, float *scales,
+                                   float *quats, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && sh_bases >= 1 && dc_stride >= 3);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(rows && means && features_dc && opacities && scales && quats);
+    GSB_CHECK_ARG(sh_bases == 1 || (features_rest != nullptr && rest_stride >= 3 * (sh_bases - 1)));
+    const int rf = gsb_ply_row_floats(sh_bases);
+    const long long total = (long long)n * rf;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (1 << 20)) blocks = 1 << 20;
+    unpack_ply_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        total, rf, sh_bases, rows, make_crs(keep_crs, crs_scale, crs_translation), means, features_dc, dc_stride,
+        features_rest, rest_stride, opacities, scales, quats);
     GSB_LAUNCH_CHECK();
     return 0;
 }

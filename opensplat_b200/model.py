@@ -15,7 +15,7 @@ import torch
 
 from . import capi, ops
 from .densify import Densifier, RefineConfig
-from .export import SceneWriter
+from .export import SceneWriter, load_ply
 
 
 def projection_matrix(z_near, z_far, fov_x, fov_y, device):
@@ -171,3 +171,14 @@ class GaussianModel:
         self.writer.save(filename, p, step, keep_crs, scale, translation)
         if wait:
             self.writer.wait()
+
+    def load_ply(self, filename, keep_crs=False, scale=1.0, translation=(0.0, 0.0, 0.0)):
+        """Model::loadPly (model.cpp:614-778): replaces the parameters, re-creates the optimizers, returns the step
+        recorded in the file (the reference resumes training from it, opensplat.cpp:139-147)."""
+        p, step = load_ply(filename, self.device, keep_crs, scale, translation)
+        for k in PARAM_NAMES:
+            setattr(self, k, p[k].requires_grad_())
+        self.shDegree = ops.deg_from_sh(self.featuresRest.shape[1] + 1)
+        self.setup_optimizers()
+        self.densifier.xys_grad_norm = self.densifier.vis_counts = self.densifier.max_2d_size = None
+        return step

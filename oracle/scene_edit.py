@@ -162,6 +162,27 @@ def ply_body(means, features_dc, features_rest, opacities, scales, quats, keep_c
     return rows.contiguous().numpy().astype("<f4").tobytes()
 
 
+def ply_load(blob, keep_crs=False, scale=1.0, translation=(0.0, 0.0, 0.0)):
+    """Model::loadPly's data path (model.cpp:724-746) on a file produced by ply_header + ply_body:
+    returns (dict of the six tensors, step)."""
+    end = blob.index(b"end_header\n") + len(b"end_header\n")
+    lines = blob[:end].decode().split("\n")
+    step = int(lines[2].rsplit(" ", 1)[1])
+    n = int(lines[3].rsplit(" ", 1)[1])
+    n_rest = sum(1 for l in lines if l.startswith("property float f_rest_"))
+    rows = torch.from_numpy(np.frombuffer(blob[end:], "<f4").reshape(n, 17 + n_rest).copy())
+    means, dc = rows[:, 0:3].clone(), rows[:, 6:9].clone()
+    rest = rows[:, 9:9 + n_rest].clone()
+    opac = rows[:, 9 + n_rest:10 + n_rest].clone()
+    sc = rows[:, 10 + n_rest:13 + n_rest].clone()
+    q = rows[:, 13 + n_rest:17 + n_rest].clone()
+    if keep_crs:
+        means = (means - _t(np.asarray(translation, dtype=np.float32))) * scale
+        sc = torch.log(scale * torch.exp(sc))
+    rest = rest.reshape(n, 3, n_rest // 3).transpose(2, 1).contiguous()
+    return {"means": means, "scales": sc, "quats": q, "featuresDc": dc, "featuresRest": rest, "opacities": opac}, step
+
+
 def splat_rows(means, features_dc, opacities, scales, quats, keep_crs=False, scale=1.0,
                translation=(0.0, 0.0, 0.0)):
     """model.cpp:560-583 -> (unordered rows as a [n,32] uint8 array, sort key [n] f32)."""

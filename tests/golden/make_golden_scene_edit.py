@@ -73,6 +73,11 @@ def save_case(name, n, k, seed, keep_crs, scale, translation):
             fn = os.path.join(d, "scene." + ext)
             REF.save(params, fn, 7000, keep_crs, scale, t(np.asarray(translation, np.float32)))
             out[ext] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+        # ... and what the reference's own Model::loadPly makes of its file (resume path)
+        ld = REF.load(os.path.join(d, "scene.ply"), keep_crs, scale, t(np.asarray(translation, np.float32)), torch.zeros(1))
+        out["ld_step"] = np.array(int(ld[0]))
+        for i, x in enumerate(PARAM_NAMES):
+            out["ld_" + x] = ld[1 + i].numpy()
     np.savez_compressed(os.path.join(OUT, name + ".npz"), n=n, k=k, seed=seed, keep_crs=keep_crs, scale=scale,
                         translation=np.asarray(translation, np.float32), step=7000, **out)
     print(name, {k_: v_.size for k_, v_ in out.items()})

@@ -8,6 +8,7 @@
 //   after_train   -> Model::afterTrain  (model.cpp:311-500), incl. the Adam-state surgery
 //   save          -> Model::save        (model.cpp:496-594; .ply or .splat by extension)
 //   train         -> the body of the reference's training loop (opensplat.cpp:151-170) for a few steps
+//   load          -> Model::loadPly     (model.cpp:614-778)
 // Nothing of the reference is copied: a Model is constructed through its own constructor (with a stub for the
 // nanoflann-based PointsTensor::scales(), whose result we overwrite anyway), its public tensors are replaced by the
 // caller's, its optimizers are re-created by its own setupOptimizers(), and the Adam moments are injected as the
@@ -164,6 +165,18 @@ std::vector<Tensor> train(std::vector<Tensor> params, Tensor camToWorlds, Tensor
     return out;
 }
 
+// Model::loadPly (model.cpp:614-778) -> {step (int64 scalar), means, scales, quats, featuresDc, featuresRest, opacities}
+std::vector<Tensor> load(std::string filename, bool keepCrs, double scale, Tensor translation, Tensor like) {
+    std::vector<Tensor> dummy = {torch::zeros({1, 3}, like.options()), torch::zeros({1, 3}, like.options()),
+                                 torch::ones({1, 4}, like.options()),  torch::zeros({1, 3}, like.options()),
+                                 torch::zeros({1, 15, 3}, like.options()), torch::zeros({1, 1}, like.options())};
+    auto m = make_model(dummy, 1, 100, 500, 30, 0.0002, 0.01, 4000, 0.05, 30000, keepCrs, scale, translation);
+    const int step = m->loadPly(filename);
+    return {torch::tensor((int64_t)step),      m->means.detach().clone(),        m->scales.detach().clone(),
+            m->quats.detach().clone(),         m->featuresDc.detach().clone(),   m->featuresRest.detach().clone(),
+            m->opacities.detach().clone()};
+}
+
 }  // namespace
 
 #ifndef GSB_DRIVER_LIB
@@ -174,4 +187,5 @@ TORCH_LIBRARY(GSB_DRIVER_LIB, m) {
     m.def("after_train", &after_train);
     m.def("save", &save);
     m.def("train", &train);
+    m.def("load", &load);
 }

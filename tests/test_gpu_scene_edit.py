@@ -289,3 +289,29 @@ def test_pipeline_resize_gaussians_keeps_rendering():
     l1 = float(pipe.train_step())
     l2 = float(pipe.train_step())
     assert np.isfinite([l0, l1, l2]).all() and pipe.m > 0
+
+
+@pytest.mark.parametrize("name", ["scene_edit_save", "scene_edit_save_crs"])
+def test_load_ply_matches_reference_loadply(name, tmp_path):
+    """export.load_ply (device unpack) == Model::loadPly on the reference's own file; save -> load round trip."""
+    from opensplat_b200 import export
+    g = load_golden(name)
+    keep, scale, tr = bool(g["keep_crs"]), float(g["scale"]), tuple(float(x) for x in g["translation"])
+    fn = str(tmp_path / "ref.ply")
+    open(fn, "wb").write(g["ply"].tobytes())
+    p, step = export.load_ply(fn, DEV, keep, scale, tr)
+    assert step == int(g["ld_step"])
+    for x in PARAM_NAMES:
+        a, b = p[x].cpu(), torch.from_numpy(g["ld_" + x])
+        if keep and x == "scales":
+            assert close(a, b)                       # log(scale * exp(s)) through device expf / logf
+        else:
+            assert torch.equal(a, b), x
+    if not keep:                                     # round trip through our own writer is the identity
+        fn2 = str(tmp_path / "ours.ply")
+        export.SceneWriter(DEV).save(fn2, p, step=step).wait()
+        assert open(fn2, "rb").read() == g["ply"].tobytes()
+    with open(fn, "ab") as f:
+        f.write(b"\0\0\0\0")
+    with pytest.raises(ValueError):
+        export.load_ply(fn, DEV)

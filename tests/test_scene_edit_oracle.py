@@ -113,3 +113,28 @@ def test_scene_writers_match_reference_bytes(name):
     assert np.all(np.diff(ref_keys) <= 0)
     if len(set(key.tolist())) == n:
         assert body == g["splat"].tobytes()
+
+
+@pytest.mark.parametrize("name", ["scene_edit_save", "scene_edit_save_crs"])
+def test_ply_loader_restatement_matches_reference_loadply(name):
+    """oracle ply_load == Model::loadPly run on the reference's own file (resume path, model.cpp:614-778)."""
+    g = load_golden(name)
+    keep, scale, tr = bool(g["keep_crs"]), float(g["scale"]), tuple(float(x) for x in g["translation"])
+    p, step = se.ply_load(g["ply"].tobytes(), keep, scale, tr)
+    assert step == int(g["ld_step"]) == int(g["step"])
+    for x in PARAM_NAMES:
+        np.testing.assert_array_equal(p[x].numpy(), g["ld_" + x], err_msg=x)
+
+
+def test_ply_header_checks_host_logic():
+    """opensplat_b200.export.parse_ply_header accepts what Model::savePly writes and rejects what loadPly rejects."""
+    from opensplat_b200.export import parse_ply_header, ply_header
+    h = ply_header(5, 16, 1234)
+    assert h == se.ply_header(5, 45, 1234)
+    assert parse_ply_header(h + b"\0" * 10) == (1234, 5, 3, 45, len(h))
+    assert parse_ply_header(ply_header(7, 1, 0))[:4] == (0, 7, 3, 0)
+    for bad in (h.replace(b"ply\n", b"plx\n", 1), h.replace(b"binary_little_endian", b"ascii"),
+                h.replace(b" at iteration 1234", b""), h.replace(b"property float nx\n", b""),
+                h.replace(b"property float rot_3\n", b""), h.replace(b"end_header\n", b"")):
+        with pytest.raises(ValueError):
+            parse_ply_header(bad)
