@@ -108,6 +108,8 @@ def cpu_reference_sample(workload, steps=1, warmup=1):
     ns, Ws, Hs = n // (div * div), W // div, H // div
     sc = make_scene(ns, Ws, Hs, scale=scale * div, sh_degree=3, opacity=opac, seed=0)
     o = ref.ops()
+    # all the host threads the reference can use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    torch.set_num_threads(max(torch.get_num_threads(), min(os.cpu_count() or 1, 64)))
     t = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).requires_grad_(g)
     target = torch.zeros(Hs, Ws, 3)
     times = []
