@@ -25,28 +25,10 @@
 #ifndef GSB_BWD_SLOT_SWITCH
 #define GSB_BWD_SLOT_SWITCH 1
 #endif
-// Experimental variant (off by default; A/B with tools/bench_blend.py): instead of one 14-shuffle butterfly per
-// (tile, Gaussian), stage the 9 per-lane partial sums of RB records in shared memory and let lane p < 9*RB sum the 32
-// lane values of (record, value) pair p with 8 bank-rotated LDS.128 (profiles/r01_blend_instruction_breakdown.md).
-// One TMA ring stage is given up so that 6 CTAs/SM still fit.
-#ifndef GSB_BWD_SMEM_REDUCE
-#define GSB_BWD_SMEM_REDUCE 0
-#endif
 
 int gsb_blend_grid(const void *kernel, int num_tiles);
 
 namespace {
-
-#if GSB_BWD_SMEM_REDUCE
-constexpr int BWD_STAGES = 3;
-constexpr int RB = 3;            // records per staged reduction: 27 (record, value) pairs <= 32 lanes
-#else
-constexpr int BWD_STAGES = RK_STAGES;
-#endif
-struct __align__(128) BwdRing {
-    GsbRecord rec[BWD_STAGES][RK_CHUNK];
-    uint64_t full[BWD_STAGES];
-};
 
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
@@ -70,34 +52,12 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                           const int *__restrict__ final_idx, const float *__restrict__ v_output,
                           const float *__restrict__ v_output_alpha, float *__restrict__ grad_rows,
                           unsigned *__restrict__ tile_counter) {
-    __shared__ BwdRing rings[RK_WARPS];
+    __shared__ WarpRing rings[RK_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    BwdRing &ring = rings[warp];
-#if GSB_BWD_SMEM_REDUCE
-    __shared__ __align__(128) float red_all[RK_WARPS][RB][9][32];
-    __shared__ int redk_all[RK_WARPS][4];
-    int nb = 0;                                           // records staged (warp-uniform); everything else is
-                                                          // recomputed inside flush() to keep the hot loop's registers
-    auto flush = [&](int cnt) {
-        __syncwarp();
-        if (lane < 9 * cnt) {
-            const int fr = lane / 9, fv = lane - 9 * fr;
-            const float4 *fbase = reinterpret_cast<const float4 *>(&red_all[warp][fr][fv][0]);
-            const int l7 = lane & 7;
-            float acc = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {                 // quarter-warp lanes hit 8 distinct 16-B bank groups
-                const float4 x = fbase[l7 ^ i];
-                acc += (x.x + x.y) + (x.z + x.w);
-            }
-            grad_rows[(size_t)redk_all[warp][fr] * GSB_GRAD_ROW_FLOATS + fv] = acc;
-        }
-        __syncwarp();
-    };
-#endif
+    WarpRing &ring = rings[warp];
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < BWD_STAGES; ++s) mbar_init(&ring.full[s], 1);
+        for (int s = 0; s < RK_STAGES; ++s) mbar_init(&ring.full[s], 1);
         mbar_fence_init();
     }
     __syncwarp();
@@ -156,8 +116,8 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
 
         // chunk c (c = 0 is the farthest) covers sorted indices [lo_c, lo_c + cnt_c)
         const unsigned g0 = gchunk;
-        auto stage_of = [&](int c) { return (g0 + (unsigned)c) % BWD_STAGES; };
-        auto parity_of = [&](int c) { return ((g0 + (unsigned)c) / BWD_STAGES) & 1u; };
+        auto stage_of = [&](int c) { return (g0 + (unsigned)c) % RK_STAGES; };
+        auto parity_of = [&](int c) { return ((g0 + (unsigned)c) / RK_STAGES) & 1u; };
         auto chunk_lo = [&](int c) { return max(range.x, hi + 1 - (c + 1) * RK_CHUNK); };
         auto chunk_cnt = [&](int c) { return (hi + 1 - c * RK_CHUNK) - chunk_lo(c); };
         auto issue = [&](int c) {
@@ -168,7 +128,7 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 tma_load_1d(&ring.rec[s][0], records + chunk_lo(c), bytes, &ring.full[s]);
             }
         };
-        const int pro = min(BWD_STAGES, nchunks);
+        const int pro = min(RK_STAGES, nchunks);
         for (int c = 0; c < pro; ++c) issue(c);
         int issued = pro;
 
@@ -259,17 +219,6 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                     if (lane < 9) row[lane] = 0.f;
                     continue;
                 }
-#if GSB_BWD_SMEM_REDUCE
-                {
-                    const float sx = dx * s0;
-                    float *dst = &red_all[warp][nb][0][lane];
-                    dst[0 * 32] = s0; dst[1 * 32] = sx; dst[2 * 32] = s1; dst[3 * 32] = dx * sx; dst[4 * 32] = dx * s1;
-                    dst[5 * 32] = s2; dst[6 * 32] = a_r; dst[7 * 32] = a_g; dst[8 * 32] = a_b;
-                    if (lane == 0) redk_all[warp][nb] = k;
-                    if (++nb == RB) { flush(RB); nb = 0; }
-                    continue;
-                }
-#endif
                 // ---- one cross-lane reduction per (tile, Gaussian): 8 values by halving, 1 by butterfly
                 const float sx = dx * s0;
                 float v0 = s0, v1 = sx, v2 = s1, v3 = dx * sx, v4 = dx * s1, v5 = s2, v6 = a_r, v7 = a_g;
@@ -307,9 +256,6 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
             __syncwarp();
             if (issued < nchunks) { issue(issued); ++issued; }
         }
-#if GSB_BWD_SMEM_REDUCE
-        if (nb) { flush(nb); nb = 0; }
-#endif
         gchunk = g0 + (unsigned)issued;
         __syncwarp();
     }
