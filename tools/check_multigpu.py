@@ -54,17 +54,17 @@ sync = parallel.replicas_in_sync(b.param_flat, world)
 # decisions identical): new flat layout + new symmetric buffers, and the fused exchange keeps matching plain NCCL
 do_resize = "--resize" in sys.argv
 ok2 = True
-keep = torch.arange(0, n, 2 if do_resize else 1, device=dev)
-idx = torch.cat([keep, keep[:1000]]) if do_resize else keep
-o, views_m, views_v = 0, {}, {}
-for name, shp in b.sizes:
-    c = int(torch.Size(shp).numel())
-    views_m[name], views_v[name] = b.adam_m[o:o + c].view(shp), b.adam_v[o:o + c].view(shp)
-    o += c
-newp = {k: v[idx].clone() for k, v in b.p.items()}
-newm = {k: v[idx].clone() for k, v in views_m.items()}
-newv = {k: v[idx].clone() for k, v in views_v.items()}
 if do_resize:
+    keep = torch.arange(0, n, 2, device=dev)
+    idx = torch.cat([keep, keep[:1000]])
+    o, views_m, views_v = 0, {}, {}
+    for name, shp in b.sizes:
+        c = int(torch.Size(shp).numel())
+        views_m[name], views_v[name] = b.adam_m[o:o + c].view(shp), b.adam_v[o:o + c].view(shp)
+        o += c
+    newp = {k: v[idx].clone() for k, v in b.p.items()}
+    newm = {k: v[idx].clone() for k, v in views_m.items()}
+    newv = {k: v[idx].clone() for k, v in views_v.items()}
     b.resize_gaussians(newp, newm, newv)
     # the fused kernel derives every view's direction from the CURRENT means; give both paths the same directions
     cp = torch.from_numpy(np.asarray(cam["cam_pos"], np.float32)).to(dev)
