@@ -62,6 +62,7 @@ class GaussianModel:
         self.shDegreeInterval = int(sh_degree_interval)
         self.numDownscales, self.resolutionSchedule = int(num_downscales), int(resolution_schedule)
         self.backgroundColor = torch.tensor(background, dtype=torch.float32, device=self.device)
+        self.group = group
         self.densifier = Densifier(self.cfg, generator=generator, group=group)
         self.writer = None
         self.xys = self.radii = None
@@ -86,6 +87,9 @@ class GaussianModel:
     def optimizers_step(self, b1=0.9, b2=0.999, eps=1e-8):
         """torch::optim::Adam::step of the six optimizers (model.cpp:236-243); a tensor without gradient is skipped
         like torch does."""
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            from .parallel import allreduce_tensor_grads     # data-parallel over views: one flat-bucket all-reduce
+            allreduce_tensor_grads([getattr(self, k) for k in PARAM_NAMES], group=self.group)
         self.adam_t += 1
         t = self.adam_t
         L = capi.lib()

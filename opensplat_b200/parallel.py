@@ -48,3 +48,35 @@ def replicas_in_sync(param_flat, world):
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     return bool(torch.equal(lo, hi))
+
+
+def allreduce_tensor_grads(tensors, world=None, average=True, group=None):
+    """Data-parallel exchange for a model whose parameters are separate tensors (model.GaussianModel: the reference's
+    six tensors): pack every defined .grad into ONE flat bucket, one all-reduce, unpack in place.  A tensor whose
+    gradient is undefined on this rank (Model::forward returned only the background) contributes zeros, and gets
+    the reduced gradient if any rank had one -- so every replica takes the same Adam step."""
+    if world is None:
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world <= 1:
+        return
+    tensors = list(tensors)
+    if not tensors:
+        return
+    total = sum(t.numel() for t in tensors)
+    bucket = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
+    o = 0
+    for t in tensors:
+        if t.grad is not None:
+            bucket[o:o + t.numel()].copy_(t.grad.reshape(-1))
+        o += t.numel()
+    dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        bucket.mul_(1.0 / world)
+    o = 0
+    for t in tensors:
+        g = bucket[o:o + t.numel()].view_as(t)
+        if t.grad is None:
+            t.grad = g.clone()
+        else:
+            t.grad.copy_(g)
+        o += t.numel()

@@ -88,3 +88,29 @@ def test_densify_stats_sync_world2():
         assert np.array_equal(r[3], a[0] + b[0]) and np.array_equal(r[4], a[1] + b[1])
         assert np.array_equal(r[5], np.maximum(a[2], b[2]))
     assert all(np.array_equal(a[i], b[i]) for i in (3, 4, 5))       # identical on every rank
+
+
+def _grads_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    ts = [torch.randn(7, 3, requires_grad=True), torch.randn(7, 15, 3, requires_grad=True), torch.randn(7, 1, requires_grad=True)]
+    ts[0].grad = torch.full((7, 3), float(rank + 1))
+    ts[1].grad = torch.full((7, 15, 3), 10.0 * (rank + 1))
+    if rank == 0:
+        ts[2].grad = torch.full((7, 1), 5.0)          # rank 1 saw nothing: undefined gradient there
+    parallel.allreduce_tensor_grads(ts, average=True)
+    ret[rank] = [t.grad.clone().numpy() for t in ts]
+    dist.destroy_process_group()
+
+
+def test_separate_tensor_gradients_one_bucket_world2():
+    import numpy as np
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_grads_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in (0, 1):
+        assert np.all(ret[r][0] == 1.5) and np.all(ret[r][1] == 15.0) and np.all(ret[r][2] == 2.5)
