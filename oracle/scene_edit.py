@@ -11,7 +11,6 @@ Pinned against the unmodified reference model.cpp compiled into oracle/_ref (tes
 -> tests/golden/scene_edit_*.npz, checked by tests/test_oracle_vs_golden.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module."""
-import math
 
 import numpy as np
 import torch

@@ -16,7 +16,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from util import PARAM_NAMES, load_golden, scene_edit_inputs  # noqa: E402
-from test_scene_edit_oracle import cfg_of, schedule  # noqa: E402
+from test_scene_edit_oracle import cfg_of  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
