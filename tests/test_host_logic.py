@@ -63,3 +63,29 @@ def test_refine_schedule_matches_reference_defaults():
     assert sch(3000)[4] is False and sch(3100)[4] is True        # huge cull only after refineEvery * resetAlphaEvery
     assert sch(15000)[:3] == (True, False, False) and sch(14900)[1] is True
     assert RefineConfig(max_steps=30001).stop_split_at == 15000
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The last bench line measured on the B200 (profiles/r01_bench_final.json) carries every key of the bench
+    contract; guards bench.py's output format against accidental regressions between GPU runs."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = [json.loads(l) for l in open(os.path.join(root, "profiles", "r01_bench_final.json")) if l.startswith("{")]
+    assert len(lines) == 1
+    d = lines[0]
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "Mpixel/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f32"
+    assert "workload" in d["config"] and d["warmup"] >= 3 and d["n_gpus"] == 1
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "GB/s"
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    assert d["gpu_launches"] > 0
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert abs(d["value"] - 1920 * 1080 / d["ms_per_step"] / 1e3) < 1e-6 * d["value"]
