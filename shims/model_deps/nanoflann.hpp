@@ -1,4 +1,4 @@
-// oracle/ref_shims/nanoflann.hpp -- TEST INFRASTRUCTURE.  Just enough of nanoflann's names for the reference's
+// shims/model_deps/nanoflann.hpp -- BUILD SHIM (like shims/cxxopts.hpp).  Just enough of nanoflann's names for the reference's
 // kdtree_tensor.hpp:47-50 type alias to parse when model.cpp is compiled for oracle/_ref (nanoflann is a
 // FetchContent dependency of the reference, absent offline).  No k-d tree is ever built: the ref driver supplies
 // its own PointsTensor::scales() (used only by Model's constructor for the initial scales, which the driver

@@ -12,7 +12,7 @@ operator headers (and gsplat.hpp / tile_bounds.hpp / constants.hpp) resolve to T
 reference's own (quoted includes search the includer's directory first); every other reference header and
 tensor_math.cpp / optim_scheduler.cpp / ssim.cpp are compiled where they lie.  Nothing from the reference is copied
 into the repo.  nanoflann / nlohmann / OpenCV calib3d (FetchContent / system dependencies, absent offline, unused
-by model.cpp) are the name-only stand-ins in oracle/ref_shims/."""
+by model.cpp) are the name-only stand-ins in shims/model_deps/."""
 import os
 import shutil
 import subprocess
@@ -43,7 +43,7 @@ def build(force=False):
     T = os.path.dirname(torch.__file__)
     ops = os.path.join(ROOT, "opensplat_b200", "csrc", "ops")
     flags = ["-std=c++17", "-O2", "-fPIC", "-DUSE_CUDA", "-D_GLIBCXX_USE_CXX11_ABI=1", "-w",
-             f"-I{tmp}", f"-I{ops}", f"-I{os.path.join(ROOT, 'oracle', 'ref_shims')}", f"-I{T}/include",
+             f"-I{tmp}", f"-I{ops}", f"-I{os.path.join(ROOT, 'shims', 'model_deps')}", f"-I{T}/include",
              f"-I{T}/include/torch/csrc/api/include", "-I/usr/local/cuda/include", f"-I{REF}"]
     srcs = [(os.path.join(tmp, "model.cpp"), []), (os.path.join(REF, "tensor_math.cpp"), []),
             (os.path.join(REF, "optim_scheduler.cpp"), []), (os.path.join(REF, "ssim.cpp"), []),
