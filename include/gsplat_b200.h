@@ -129,30 +129,44 @@ int gsb_gather_bin_edges(int m, int num_tiles, const int64_t *isect_ids_sorted,
                          int32_t *gaussian_ids_sorted, int32_t *tile_bins, gsb_stream_t stream);
 
 /* ---- Tile binning, fast path: two-level bucket sort fused with record packing ------------------
- * Produces the SAME tile_bins and the SAME per-tile order (tile, then depth bits, ties by ascending
- * unsorted slot) as gsb_map_gaussian_to_intersects + gsb_sort_intersects + gsb_gather_bin_edges +
- * the record packing of gsb_rasterize_forward, without a global sort (what RasterizeGaussians::forward
- * needs between rasterize_gaussians.cpp:62 and :79).
- * gsb_bucket_tile_ranges (before the M read-back): tile_bins [tiles,2], tile_cursor (scratch of
- *   gsb_bucket_cursor_bytes(tiles) bytes that phase 2 consumes) and stats[2] = {M, longest tile list} (device int32; read both back in the operator's
- *   single D2H copy).
- * gsb_bucket_sort_pack (after it): fills `records` (gsb_raster_records_bytes(m)); optional outputs
- *   sorted_index [m] / gaussian_ids_sorted [m] (NULL to skip).  Returns GSB_ERR_UNSUPPORTED if
- *   max_tile_len > gsb_bucket_max_tile_len() -- take the generic path then.
- * gsb_rasterize_forward_packed: the blend kernel alone on an already packed record stream. */
+ * What RasterizeGaussians::forward needs between rasterize_gaussians.cpp:62 and :79 (cumsum, the M read-back,
+ * emit, global sort, gather, bin edges, and the record packing of gsb_rasterize_forward) without a global sort and
+ * without a host read-back in the middle of the frame.
+ * cull = 0: tile_bins, cum_tiles_hit and the per-tile order (tile, then depth bits, ties by ascending unsorted
+ *   slot) are bit-identical to gsb_cumsum_tiles_hit + gsb_map_gaussian_to_intersects + gsb_sort_intersects +
+ *   gsb_gather_bin_edges.
+ * cull = 1 (what the operator uses): a (Gaussian, tile) pair is binned only if the Gaussian's extent box
+ *   {pixels where opacity * exp(-sigma) can reach 1/255} touches the tile -- exactly the test the blend kernels
+ *   apply per record, so no pixel or gradient changes; M, tile_bins and cum_tiles_hit then describe the culled
+ *   lists (internal to the operator: the reference's RasterizeGaussians does not return them).
+ * Capacities: the caller sizes `workspace` (gsb_bucket_workspace_bytes(n, m_capacity, tiles)), `records`
+ *   (gsb_raster_records_bytes(m_capacity)) and the sort's shared memory (len_capacity <= gsb_bucket_max_tile_len())
+ *   from earlier frames; stats (device int32[4]) = {M, longest tile list, overflow, 0} with overflow = 1 iff
+ *   M > m_capacity or longest > len_capacity, in which case gsb_bucket_sort_pack and
+ *   gsb_rasterize_forward_packed (given the same stats pointer) do nothing: the host reads stats back AFTER
+ *   enqueuing the whole forward pass and, on overflow, repeats the three calls with larger capacities.
+ *   Exact-size use: m_capacity = M, len_capacity = longest list of a previous gsb_bucket_tile_ranges call.
+ * gsb_bucket_tile_ranges: builds the per-Gaussian attribute records (in the workspace), counts and scans:
+ *   cum_tiles_hit [n] (inclusive scan of the per-Gaussian binned-tile counts = the gradient-row slots of
+ *   gsb_rasterize_backward), tile_bins [tiles,2] (empty tiles (0,0)), stats.
+ * gsb_bucket_sort_pack: fills `records`; optional outputs sorted_index [M] / gaussian_ids_sorted [M] (NULL to
+ *   skip).  Returns GSB_ERR_UNSUPPORTED if len_capacity > gsb_bucket_max_tile_len() -- take the generic path.
+ * gsb_rasterize_forward_packed: the blend kernel alone on an already packed record stream; m = the m_capacity
+ *   the records buffer was sized with; bin_stats may be NULL. */
 int gsb_bucket_max_tile_len(void);
-size_t gsb_bucket_cursor_bytes(int num_tiles);
-size_t gsb_bucket_workspace_bytes(int n, int m);
-int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
-                           int32_t *tile_bins, int32_t *tile_cursor, int32_t *stats, gsb_stream_t stream);
-int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float *xys, const float *depths,
-                         const int32_t *radii, const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
-                         const int32_t *tile_bins, int32_t *tile_cursor, const float *conics, const float *colors,
-                         const float *opacities, void *workspace, size_t workspace_bytes, void *records,
+size_t gsb_bucket_workspace_bytes(int n, int m_capacity, int num_tiles);
+int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, const float *conics, const float *colors,
+                           const float *opacities, int cull, int tiles_x, int tiles_y, int m_capacity,
+                           int len_capacity, void *workspace, size_t workspace_bytes, int32_t *cum_tiles_hit,
+                           int32_t *tile_bins, int32_t *stats, gsb_stream_t stream);
+int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, const float *depths, const int32_t *radii,
+                         const int32_t *cum_tiles_hit, int cull, int tiles_x, int tiles_y, const int32_t *tile_bins,
+                         const int32_t *stats, void *workspace, size_t workspace_bytes, void *records,
                          int32_t *sorted_index, int32_t *gaussian_ids_sorted, gsb_stream_t stream);
 int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, int tiles_y, int m,
-                                 const int32_t *tile_bins, const float *background, void *records,
-                                 float *out_img, float *final_Ts, int32_t *final_idx, gsb_stream_t stream);
+                                 const int32_t *tile_bins, const int32_t *bin_stats, const float *background,
+                                 void *records, float *out_img, float *final_Ts, int32_t *final_idx,
+                                 gsb_stream_t stream);
 
 /* ---- Rasterization ---------------------------------------------------------------------------
  * gsb_rasterize_forward replaces rasterize_forward_tensor (bindings.h:110-125, bindings.cu:338-410,

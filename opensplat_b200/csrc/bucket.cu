@@ -1,19 +1,30 @@
-// bucket.cu -- two-level tile binning fused with record packing (fast path of B2+B3+B4 + pack).
+// bucket.cu -- two-level tile binning fused with record packing (fast path of B1+B2+B3+B4 + pack).
 //
-// The reference sorts all M intersections globally on the 64-bit key (tile_id << 32 | depth bits)
-// (rasterize_gaussians.cpp:25-32) and then finds tile boundaries (forward.cu:148-169).  The same
-// ORDER -- by tile, then depth bits, ties by ascending unsorted slot k (what a stable sort of the
-// Gaussian-major emission gives) -- is produced here without a global sort:
-//   K1 tile_count   : per Gaussian, one atomic per covered tile  -> tile sizes
-//   K2 tile_scan    : exclusive scan over the T tiles            -> tile_bins (first, last+1) directly, max length
-//   K3 bucket_emit  : per Gaussian, write (depth bits << 32 | k) into its tiles' segments (atomic cursor;
-//                     arrival order is arbitrary, the composite key makes the final order unique)
-//   K4 tile_sort_pack: one CTA per tile sorts its segment in shared memory (bitonic, 64-bit composites),
-//                     then gathers the Gaussian attributes and writes the 48-B record stream directly.
-// Per-intersection HBM traffic drops from (8 + 6*24 + 8 + 12 + 84) B of the emit / 6-pass radix / bins /
-// pack sequence to 8 B written + 8 B read of composites (L2-resident) + 36 B gathered + 48 B written.
-// Integer work, L2/HBM-bound; results (tile_bins, per-tile order) are bit-identical to the generic
-// path (tests/test_gpu_parity.py::test_bucket_binning_matches_generic_sort).
+// The reference scans num_tiles_hit (rasterize_gaussians.cpp:62), reads M back (:63), sorts all M intersections
+// globally on the 64-bit key (tile_id << 32 | depth bits) (:25-32) and then finds tile boundaries
+// (forward.cu:148-169).  The same ORDER -- by tile, then depth bits, ties by ascending unsorted slot k (what a
+// stable sort of the Gaussian-major emission gives) -- is produced here without a global sort and without a
+// host read-back in the middle:
+//   K1 bin_count_scan : per Gaussian, build its 48-B attribute record once, count the tiles it is binned to (one
+//                       atomic per tile -> tile sizes) and scan the per-Gaussian counts in the same kernel
+//                       (single-pass chained scan, decoupled look-back) -> cum_tiles_hit (the gradient-row slots)
+//   K2 tile_scan      : exclusive scan over the T tiles (chained scan over <= 32 CTAs) -> tile_bins (first, last+1),
+//                       write cursors, stats = {M, longest list, overflow flag}
+//   K3 bucket_emit    : per Gaussian, write (depth bits << 32 | k) into its tiles' segments (atomic cursor;
+//                       arrival order is arbitrary, the composite key makes the final order unique)
+//   K4 tile_sort_pack : one CTA per tile sorts its segment in shared memory (64-bit composites), then gathers the
+//                       Gaussian attributes and writes the 48-B record stream directly.
+// Optional conservative culling (cull = 1, what RasterizeGaussians uses): a (Gaussian, tile) pair is binned only
+// if the Gaussian's extent box {alpha can reach 1/255} touches the tile -- the same test, on the same floats, that
+// the blend kernels apply per record (extent_slot_mask), so no pixel result changes; it removes 20-25 % of the
+// intersections from the sort, the record stream and the gradient rows.  With cull = 0 tile_bins, cum_tiles_hit
+// and the per-tile order are bit-identical to the reference's / the generic path's
+// (tests/test_gpu_parity.py::test_bucket_binning_matches_generic_sort).
+// K2-K4 and the blend kernels are sized by CAPACITIES chosen by the host from earlier frames; K2 raises
+// stats[2] when M or the longest list exceeds them and everything downstream then returns immediately, so the
+// host can check the read-back AFTER it has enqueued the whole forward pass (no pipeline bubble) and redo the
+// frame with larger buffers in the rare overflow case.
+// Integer work, L2/HBM-bound.
 #include "raster_common.cuh"
 
 namespace {
@@ -21,6 +32,18 @@ namespace {
 // Tile counters / write cursors are padded to one 128-B line each: the ~400 atomics a tile receives then
 // serialise in their own L2 line (and the lines spread over all L2 slices) instead of 32 tiles sharing one.
 constexpr int CUR_STRIDE = 32;  // ints
+constexpr int BIN_THREADS = 256;
+constexpr int TSCAN_THREADS = 1024;
+
+struct BinHeader {          // 256 B at the start of the workspace, zeroed by the call's memset
+    unsigned ticket_n;      // dynamic block ids of K1 (order of the chained scan)
+    unsigned ticket_t;      // ... of K2
+    unsigned done_t;        // K2 blocks finished
+    int max_len;            // longest tile list (atomicMax)
+    int total;              // M
+    int pad[59];
+};
+static_assert(sizeof(BinHeader) == 256, "header is 256 bytes");
 
 __device__ __forceinline__ void tile_bbox_of(float2 c, int r, int tiles_x, int tiles_y, int &x0, int &x1, int &y0,
                                              int &y1) {
@@ -32,104 +55,192 @@ __device__ __forceinline__ void tile_bbox_of(float2 c, int r, int tiles_x, int t
     y1 = min(max(0, (int)(tcy + tr + 1.f)), tiles_y);
 }
 
-__global__ void __launch_bounds__(256)
-tile_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii, int tiles_x,
-                  int tiles_y, int *__restrict__ tile_count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int r = radii[i];
-    if (r <= 0) return;
-    int x0, x1, y0, y1;
-    tile_bbox_of(xys[i], r, tiles_x, tiles_y, x0, x1, y0, y1);
-    for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) atomicAdd(&tile_count[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
+__device__ __forceinline__ int warp_incl_scan_i(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
 }
 
-// single CTA: exclusive scan of tile_count -> tile_bins, write cursors, max tile length.
-// Each thread owns 8 consecutive tiles per trip (all 8 strided loads issued before use).
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(int T, int *__restrict__ tile_count_then_cursor, int2 *__restrict__ tile_bins,
-                 int *__restrict__ stats /* [0] = total, [1] = max length */) {
-    __shared__ int sm[33];
-    __shared__ int s_max;
+// block-wide exclusive scan of one int per thread; *total = block sum.  smem: THREADS/32 + 1 ints.
+template <int THREADS>
+__device__ __forceinline__ int block_excl_scan_i(int v, int *total, int *smem) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_max = 0;
+    const int inc = warp_incl_scan_i(v);
+    if (lane == 31) smem[w] = inc;
     __syncthreads();
-    int carry = 0, my_max = 0;
-    for (int base = 0; base < T; base += 8192) {
-        const int i0 = base + threadIdx.x * 8;
-        int v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (i0 + k < T) ? tile_count_then_cursor[(size_t)(i0 + k) * CUR_STRIDE] : 0;
-        int tsum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { tsum += v[k]; my_max = max(my_max, v[k]); }
-        int inc = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) sm[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            int x = sm[lane];
-            int xi = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, xi, o);
-                if (lane >= o) xi += t;
-            }
-            sm[lane] = xi - x;
-            if (lane == 31) sm[32] = xi;
-        }
-        __syncthreads();
-        int excl = carry + sm[w] + inc - tsum;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i0 + k < T) {
-                // empty tiles keep (0,0) like the reference's zero-initialised tile_bins
-                tile_bins[i0 + k] = (v[k] > 0) ? make_int2(excl, excl + v[k]) : make_int2(0, 0);
-                tile_count_then_cursor[(size_t)(i0 + k) * CUR_STRIDE] = excl;  // becomes the write cursor of K3
-            }
-            excl += v[k];
-        }
-        carry += sm[32];
-        __syncthreads();
+    if (w == 0) {
+        const int x = (lane < THREADS / 32) ? smem[lane] : 0;
+        const int xi = warp_incl_scan_i(x);
+        if (lane < THREADS / 32) smem[lane] = xi - x;
+        if (lane == 31) smem[THREADS / 32] = xi;
     }
-    atomicMax(&s_max, my_max);
     __syncthreads();
+    const int res = smem[w] + inc - v;
+    *total = smem[THREADS / 32];
+    __syncthreads();
+    return res;
+}
+
+// ---- single-pass chained scan across blocks (decoupled look-back) ------------------------------------------
+// state[b] = flag << 62 | value: flag 1 = block aggregate published, 2 = inclusive prefix published.  Blocks take
+// their index from a ticket counter, so every block a look-back waits on is already running.
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = 0xffffffffull;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Called by the first warp of a block; returns (to every lane) the sum of the aggregates of blocks 0..blk-1 and
+// publishes this block's inclusive prefix.
+__device__ __forceinline__ int chained_scan_prefix(unsigned long long *state, int blk, int aggregate) {
+    const int lane = threadIdx.x & 31;
+    if (blk == 0) {
+        if (lane == 0) st_state(&state[0], ST_INC | (unsigned)aggregate);
+        return 0;
+    }
+    if (lane == 0) st_state(&state[blk], ST_AGG | (unsigned)aggregate);
+    int excl = 0;
+    int j = blk - 1;
+    while (true) {
+        const int idx = j - lane;
+        unsigned long long s = ST_INC;   // virtual block -1: inclusive prefix 0
+        if (idx >= 0) s = ld_state(&state[idx]);
+        const unsigned flag = (unsigned)(s >> 62);
+        if (__ballot_sync(0xffffffffu, flag == 0u)) continue;   // a predecessor has not published yet: poll again
+        const unsigned incm = __ballot_sync(0xffffffffu, flag == 2u);
+        int val = (int)(unsigned)(s & ST_VAL);
+        if (incm) {
+            const int first = __ffs(incm) - 1;      // nearest predecessor with an inclusive prefix
+            if (lane > first) val = 0;
+            excl += __reduce_add_sync(0xffffffffu, val);
+            break;
+        }
+        excl += __reduce_add_sync(0xffffffffu, val);
+        j -= 32;
+    }
+    if (lane == 0) st_state(&state[blk], ST_INC | (unsigned)(excl + aggregate));
+    return excl;
+}
+
+// K1: attribute record + tile counting + per-Gaussian scan
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_count_scan_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii,
+                      const float *__restrict__ conics, const float *__restrict__ colors,
+                      const float *__restrict__ opacities, int cull, int tiles_x, int tiles_y, BinHeader *hdr,
+                      unsigned long long *state, int *__restrict__ tile_count, GsbRecord *__restrict__ gattr,
+                      int *__restrict__ cum_out) {
+    __shared__ int sm[BIN_THREADS / 32 + 1];
+    __shared__ int s_blk, s_prefix;
+    if (threadIdx.x == 0) s_blk = (int)atomicAdd(&hdr->ticket_n, 1u);
+    __syncthreads();
+    const int blk = s_blk;
+    const int i = blk * BIN_THREADS + threadIdx.x;
+    int cnt = 0;
+    if (i < n) {
+        const int r = radii[i];
+        if (r > 0) {
+            const float2 c = xys[i];
+            // the record of this Gaussian is built ONCE here (log2 / sqrt / extents) and only copied per intersection
+            const GsbRecord rec = make_record(c, __ldg(conics + 3 * i), __ldg(conics + 3 * i + 1),
+                                              __ldg(conics + 3 * i + 2), __ldg(opacities + i), __ldg(colors + 3 * i),
+                                              __ldg(colors + 3 * i + 1), __ldg(colors + 3 * i + 2), 0);
+            float4 *dst = reinterpret_cast<float4 *>(gattr + i);
+            dst[0] = rec.q0; dst[1] = rec.q1; dst[2] = rec.q2;
+            int x0, x1, y0, y1;
+            tile_bbox_of(c, r, tiles_x, tiles_y, x0, x1, y0, y1);
+            for (int ty = y0; ty < y1; ++ty)
+                for (int tx = x0; tx < x1; ++tx) {
+                    if (cull && !extent_slot_mask(c.x, c.y, rec.q1.w, rec.q2.w, (float)(tx * GSB_TILE),
+                                                  (float)(ty * GSB_TILE)))
+                        continue;
+                    atomicAdd(&tile_count[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
+                    ++cnt;
+                }
+        }
+    }
+    int total;
+    const int excl = block_excl_scan_i<BIN_THREADS>(cnt, &total, sm);
+    if (threadIdx.x < 32) {
+        const int p = chained_scan_prefix(state, blk, total);
+        if (threadIdx.x == 0) s_prefix = p;
+    }
+    __syncthreads();
+    if (i < n) cum_out[i] = s_prefix + excl + cnt;
+}
+
+// K2: exclusive scan of the tile sizes -> tile_bins, write cursors, stats = {M, longest list, overflow, 0}
+__global__ void __launch_bounds__(TSCAN_THREADS)
+tile_scan_kernel(int T, int nblk, int m_capacity, int len_capacity, BinHeader *hdr, unsigned long long *state,
+                 int *__restrict__ tile_count_then_cursor, int2 *__restrict__ tile_bins, int *__restrict__ stats) {
+    __shared__ int sm[TSCAN_THREADS / 32 + 1];
+    __shared__ int s_blk, s_prefix, s_max;
+    if (threadIdx.x == 0) { s_blk = (int)atomicAdd(&hdr->ticket_t, 1u); s_max = 0; }
+    __syncthreads();
+    const int blk = s_blk;
+    const int t = blk * TSCAN_THREADS + threadIdx.x;
+    const int v = (t < T) ? tile_count_then_cursor[(size_t)t * CUR_STRIDE] : 0;
+    int total;
+    const int excl = block_excl_scan_i<TSCAN_THREADS>(v, &total, sm);
+    const int wmax = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(&s_max, wmax);
+    if (threadIdx.x < 32) {
+        const int p = chained_scan_prefix(state, blk, total);
+        if (threadIdx.x == 0) s_prefix = p;
+    }
+    __syncthreads();
+    if (t < T) {
+        const int e = s_prefix + excl;
+        // empty tiles keep (0,0) like the reference's zero-initialised tile_bins
+        tile_bins[t] = (v > 0) ? make_int2(e, e + v) : make_int2(0, 0);
+        tile_count_then_cursor[(size_t)t * CUR_STRIDE] = e;   // becomes the write cursor of K3
+    }
     if (threadIdx.x == 0) {
-        stats[0] = carry;
-        stats[1] = s_max;
+        if (s_max > 0) atomicMax(&hdr->max_len, s_max);
+        if (blk == nblk - 1) atomicExch(&hdr->total, s_prefix + total);
+        __threadfence();
+        const unsigned done = atomicAdd(&hdr->done_t, 1u);
+        if (done == (unsigned)nblk - 1u) {   // every block has published its part
+            __threadfence();
+            const int M = atomicAdd(&hdr->total, 0), mx = atomicAdd(&hdr->max_len, 0);
+            stats[0] = M;
+            stats[1] = mx;
+            stats[2] = (M > m_capacity || mx > len_capacity) ? 1 : 0;
+            stats[3] = 0;
+        }
     }
 }
 
+// K3: write the composites (depth bits << 32 | k) into the tiles' segments
 __global__ void __launch_bounds__(256)
-bucket_emit_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__ depths,
-                   const int *__restrict__ radii, const int *__restrict__ cum_tiles_hit, int tiles_x,
+bucket_emit_kernel(int n, const GsbRecord *__restrict__ gattr, const float *__restrict__ depths,
+                   const int *__restrict__ radii, const int *__restrict__ cum_tiles_hit, int cull, int tiles_x,
                    int tiles_y, int *__restrict__ cursor, unsigned long long *__restrict__ comp,
-                   int *__restrict__ gaussian_ids, const float *__restrict__ conics,
-                   const float *__restrict__ colors, const float *__restrict__ opacities,
-                   GsbRecord *__restrict__ gattr) {
+                   int *__restrict__ gaussian_ids, const int *__restrict__ stats) {
+    if (stats[2]) return;   // capacities exceeded: the host redoes the frame
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int r = radii[i];
     if (r <= 0) return;
-    // the record of this Gaussian is built ONCE here (log2 / sqrt / extents) and only copied per intersection
-    {
-        const GsbRecord rec = make_record(xys[i], __ldg(conics + 3 * i), __ldg(conics + 3 * i + 1),
-                                          __ldg(conics + 3 * i + 2), __ldg(opacities + i), __ldg(colors + 3 * i),
-                                          __ldg(colors + 3 * i + 1), __ldg(colors + 3 * i + 2), 0);
-        float4 *dst = reinterpret_cast<float4 *>(gattr + i);
-        dst[0] = rec.q0; dst[1] = rec.q1; dst[2] = rec.q2;
-    }
+    const float4 *src = reinterpret_cast<const float4 *>(gattr + i);
+    const float4 q0 = src[0];
+    const float hx = src[1].w, hy = src[2].w;
     int x0, x1, y0, y1;
-    tile_bbox_of(xys[i], r, tiles_x, tiles_y, x0, x1, y0, y1);
+    tile_bbox_of(make_float2(q0.x, q0.y), r, tiles_x, tiles_y, x0, x1, y0, y1);
     int k = (i == 0) ? 0 : cum_tiles_hit[i - 1];
     const unsigned long long hi = ((unsigned long long)(unsigned)__float_as_int(depths[i])) << 32;
     for (int ty = y0; ty < y1; ++ty)
         for (int tx = x0; tx < x1; ++tx) {
+            if (cull && !extent_slot_mask(q0.x, q0.y, hx, hy, (float)(tx * GSB_TILE), (float)(ty * GSB_TILE)))
+                continue;
             const int pos = atomicAdd(&cursor[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
             comp[pos] = hi | (unsigned)k;
             gaussian_ids[k] = i;
@@ -259,11 +370,12 @@ __global__ void __launch_bounds__(256)
 tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
                       const int *__restrict__ gaussian_ids, const GsbRecord *__restrict__ gattr,
                       GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
-                      int *__restrict__ gaussian_ids_sorted) {
+                      int *__restrict__ gaussian_ids_sorted, const int *__restrict__ stats) {
     extern __shared__ unsigned long long skey[];
     __shared__ unsigned whist[8][256];
     __shared__ unsigned bin_base[256 + 8];
     __shared__ unsigned s_flag;
+    if (stats[2]) return;      // capacities exceeded: the host redoes the frame
     const int tile = blockIdx.x;
     const int2 range = tile_bins[tile];
     const int L = range.y - range.x;
@@ -271,7 +383,7 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
     int n2 = 64;               // padded length: 64 (bitonic) or a multiple of 256 (radix), power of two
     while (n2 < L) n2 <<= 1;
     if (n2 > 64 && n2 < 256) n2 = 256;
-    if (n2 > cap) return;      // host guarantees max length <= cap (otherwise it takes the generic path)
+    if (n2 > cap) return;      // cannot happen: K2 raised stats[2] if a list is longer than the capacity
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) skey[i] = (i < L) ? comp[range.x + i] : ~0ull;
     __syncthreads();
@@ -361,74 +473,94 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
 }
 
 struct BucketLayout {
-    size_t comp, gids, gattr, total;
+    size_t hdr, state_n, state_t, cursor, zero_bytes, gattr, comp, gids, total;
+    int nblk_n, nblk_t;
 };
-BucketLayout bucket_layout(int n, int m) {
+BucketLayout bucket_layout(int n, int m, int T) {
     BucketLayout L;
+    L.nblk_n = gsb_div_up(n > 0 ? n : 1, BIN_THREADS);
+    L.nblk_t = gsb_div_up(T > 0 ? T : 1, TSCAN_THREADS);
     size_t o = 0;
+    L.hdr = o; o += sizeof(BinHeader);
+    L.state_n = o; o += gsb_align_up((size_t)L.nblk_n * 8, 256);
+    L.state_t = o; o += gsb_align_up((size_t)L.nblk_t * 8, 256);
+    L.cursor = o; o += gsb_align_up((size_t)(T > 0 ? T : 1) * CUR_STRIDE * sizeof(int), 256);
+    L.zero_bytes = o;   // everything up to here is zeroed by one memset per call
+    L.gattr = o; o += gsb_align_up((size_t)n * sizeof(GsbRecord), 256);
     L.comp = o; o += gsb_align_up((size_t)m * 8, 256);
     L.gids = o; o += gsb_align_up((size_t)m * 4, 256);
-    L.gattr = o; o += gsb_align_up((size_t)n * sizeof(GsbRecord), 256);
     L.total = o;
     return L;
 }
 
 constexpr int BUCKET_MAX_CAP = 16384;  // 128 KB of shared memory per CTA
 
+int sort_cap_of(int len_capacity) {   // shared-memory capacity (power of two) of K4 for lists up to len_capacity
+    int cap = 64;
+    while (cap < len_capacity && cap < (1 << 30)) cap <<= 1;
+    if (cap > 64 && cap < 256) cap = 256;
+    return cap;
+}
+
 }  // namespace
 
 extern "C" int gsb_bucket_max_tile_len(void) { return BUCKET_MAX_CAP; }
 
-extern "C" size_t gsb_bucket_cursor_bytes(int num_tiles) {
-    return (size_t)(num_tiles > 0 ? num_tiles : 1) * CUR_STRIDE * sizeof(int);
+extern "C" size_t gsb_bucket_workspace_bytes(int n, int m_capacity, int num_tiles) {
+    return bucket_layout(n > 0 ? n : 0, m_capacity > 0 ? m_capacity : 0, num_tiles).total;
 }
 
-extern "C" size_t gsb_bucket_workspace_bytes(int n, int m) {
-    return bucket_layout(n > 0 ? n : 0, m > 0 ? m : 0).total + 256;
-}
-
-// Phase 1 (before the M read-back): tile sizes -> tile_bins, tile_cursor (gsb_bucket_cursor_bytes(tiles); the
-// padded write cursors for phase 2),
-// stats = {M, max tile length} (device int32[2]).
-extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
-                                      int32_t *tile_bins, int32_t *tile_cursor, int32_t *stats,
-                                      gsb_stream_t stream) {
-    GSB_CHECK_ARG(n >= 0 && tiles_x > 0 && tiles_y > 0 && tile_bins && tile_cursor && stats);
+// Phase 1: attribute records, tile sizes -> tile_bins + write cursors (inside the workspace), the scan of the
+// per-Gaussian tile counts and stats = {M, longest list, overflow, 0} (device int32[4]).
+extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, const float *conics,
+                                      const float *colors, const float *opacities, int cull, int tiles_x,
+                                      int tiles_y, int m_capacity, int len_capacity, void *workspace,
+                                      size_t workspace_bytes, int32_t *cum_tiles_hit, int32_t *tile_bins,
+                                      int32_t *stats, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && tiles_x > 0 && tiles_y > 0 && m_capacity >= 0 && len_capacity >= 0);
+    GSB_CHECK_ARG(tile_bins && stats && workspace && ((uintptr_t)workspace % 256) == 0);
     const int T = tiles_x * tiles_y;
-    cudaStream_t s = (cudaStream_t)stream;
-    GSB_CUDA(cudaMemsetAsync(tile_cursor, 0, gsb_bucket_cursor_bytes(T), s));
-    if (n > 0) {
-        GSB_CHECK_ARG(xys && radii && ((uintptr_t)xys % 8) == 0);
-        tile_count_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, reinterpret_cast<const float2 *>(xys), radii,
-                                                            tiles_x, tiles_y, tile_cursor);
-    }
-    tile_scan_kernel<<<1, 1024, 0, s>>>(T, tile_cursor, reinterpret_cast<int2 *>(tile_bins), stats);
-    GSB_LAUNCH_CHECK();
-    return 0;
-}
-
-// Phase 2 (after the read-back of {M, max_len}): bucket emit + per-tile sort + record pack.  Consumes
-// (advances) tile_cursor.  sorted_index / gaussian_ids_sorted are optional outputs ([m] int32, may be NULL).
-extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float *xys, const float *depths,
-                                    const int32_t *radii, const int32_t *cum_tiles_hit, int tiles_x,
-                                    int tiles_y, const int32_t *tile_bins, int32_t *tile_cursor,
-                                    const float *conics, const float *colors, const float *opacities,
-                                    void *workspace, size_t workspace_bytes, void *records,
-                                    int32_t *sorted_index, int32_t *gaussian_ids_sorted, gsb_stream_t stream) {
-    GSB_CHECK_ARG(n >= 0 && m >= 0 && tiles_x > 0 && tiles_y > 0 && max_tile_len >= 0);
-    if (n == 0 || m == 0) return 0;
-    GSB_CHECK_ARG(xys && depths && radii && cum_tiles_hit && tile_bins && tile_cursor && conics && colors &&
-                  opacities && workspace && records);
-    GSB_CHECK_ARG(((uintptr_t)workspace % 256) == 0 && ((uintptr_t)records % 16) == 0);
-    const int T = tiles_x * tiles_y;
-    const BucketLayout L = bucket_layout(n, m);
+    const BucketLayout L = bucket_layout(n, m_capacity, T);
     if (workspace_bytes < L.total) {
         gsb_set_error(GSB_ERR_WORKSPACE, "bucket workspace too small", __FILE__, __LINE__);
         return GSB_ERR_WORKSPACE;
     }
-    int cap = 64;
-    while (cap < max_tile_len) cap <<= 1;
-    if (cap > 64 && cap < 256) cap = 256;
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    BinHeader *hdr = (BinHeader *)(ws + L.hdr);
+    int *cursor = (int *)(ws + L.cursor);
+    GSB_CUDA(cudaMemsetAsync(ws, 0, L.zero_bytes, s));
+    if (n > 0) {
+        GSB_CHECK_ARG(xys && radii && conics && colors && opacities && cum_tiles_hit && ((uintptr_t)xys % 8) == 0);
+        bin_count_scan_kernel<<<L.nblk_n, BIN_THREADS, 0, s>>>(
+            n, reinterpret_cast<const float2 *>(xys), radii, conics, colors, opacities, cull, tiles_x, tiles_y, hdr,
+            (unsigned long long *)(ws + L.state_n), cursor, (GsbRecord *)(ws + L.gattr), cum_tiles_hit);
+    }
+    tile_scan_kernel<<<L.nblk_t, TSCAN_THREADS, 0, s>>>(T, L.nblk_t, m_capacity, len_capacity, hdr,
+                                                       (unsigned long long *)(ws + L.state_t), cursor,
+                                                       reinterpret_cast<int2 *>(tile_bins), stats);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Phase 2: bucket emit + per-tile sort + record pack, sized by the same capacities as phase 1 (no host read-back
+// needed in between).  sorted_index / gaussian_ids_sorted are optional outputs ([m] int32, may be NULL).
+extern "C" int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, const float *depths,
+                                    const int32_t *radii, const int32_t *cum_tiles_hit, int cull, int tiles_x,
+                                    int tiles_y, const int32_t *tile_bins, const int32_t *stats, void *workspace,
+                                    size_t workspace_bytes, void *records, int32_t *sorted_index,
+                                    int32_t *gaussian_ids_sorted, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && m_capacity >= 0 && tiles_x > 0 && tiles_y > 0 && len_capacity >= 0);
+    if (n == 0 || m_capacity == 0) return 0;
+    GSB_CHECK_ARG(depths && radii && cum_tiles_hit && tile_bins && stats && workspace && records);
+    GSB_CHECK_ARG(((uintptr_t)workspace % 256) == 0 && ((uintptr_t)records % 16) == 0);
+    const int T = tiles_x * tiles_y;
+    const BucketLayout L = bucket_layout(n, m_capacity, T);
+    if (workspace_bytes < L.total) {
+        gsb_set_error(GSB_ERR_WORKSPACE, "bucket workspace too small", __FILE__, __LINE__);
+        return GSB_ERR_WORKSPACE;
+    }
+    const int cap = sort_cap_of(len_capacity);
     if (cap > BUCKET_MAX_CAP) {
         gsb_set_error(GSB_ERR_UNSUPPORTED, "tile list longer than the in-shared-memory sort capacity; "
                       "use the generic gsb_sort_intersects path", __FILE__, __LINE__);
@@ -439,9 +571,8 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
     unsigned long long *comp = (unsigned long long *)(ws + L.comp);
     int *gids = (int *)(ws + L.gids);
     GsbRecord *gattr = (GsbRecord *)(ws + L.gattr);
-    bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, reinterpret_cast<const float2 *>(xys), depths, radii,
-                                                         cum_tiles_hit, tiles_x, tiles_y, tile_cursor, comp, gids,
-                                                         conics, colors, opacities, gattr);
+    bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, gattr, depths, radii, cum_tiles_hit, cull, tiles_x,
+                                                         tiles_y, (int *)(ws + L.cursor), comp, gids, stats);
     const size_t smem = (size_t)cap * 8;
 #define GSB_TSP(MAXI)                                                                                           \
     do {                                                                                                        \
@@ -450,7 +581,7 @@ extern "C" int gsb_bucket_sort_pack(int n, int m, int max_tile_len, const float 
                                           (int)smem));                                                          \
         tile_sort_pack_kernel<MAXI><<<T, 256, smem, s>>>(                                                       \
             cap, reinterpret_cast<const int2 *>(tile_bins), comp, gids, gattr,                                  \
-            reinterpret_cast<GsbRecord *>(records), sorted_index, gaussian_ids_sorted);                         \
+            reinterpret_cast<GsbRecord *>(records), sorted_index, gaussian_ids_sorted, stats);                  \
     } while (0)
     if (cap <= 1024) GSB_TSP(4);
     else if (cap <= 4096) GSB_TSP(16);

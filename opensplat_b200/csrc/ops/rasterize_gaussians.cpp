@@ -4,6 +4,10 @@
 #include "rasterize_gaussians.hpp"
 #include "gsplat.hpp"
 #include "gsb_torch.hpp"
+#include <ATen/cuda/CUDAEvent.h>
+#include <algorithm>
+#include <climits>
+#include <mutex>
 
 namespace {
 
@@ -54,6 +58,54 @@ binAndSortGaussians(int numPoints, int numIntersects, torch::Tensor xys, torch::
     return std::make_tuple(b.isectIds, b.gaussianIds, b.isectIdsSorted, b.gaussianIdsSorted, b.tileBins);
 }
 
+// ---- capacity plan of the fast binning path ----------------------------------------------------
+// The reference blocks on `cumTilesHit[-1].item<int>()` (rasterize_gaussians.cpp:63) in the middle of the forward
+// pass.  Here the M-dependent buffers are sized from high-water marks of earlier frames (per device, grow-only,
+// 25 % headroom), the kernels are enqueued against those capacities and flag a frame that outgrows them, and the
+// read-back is waited for only after the whole forward pass has been enqueued; the rare overflowing frame (and the
+// very first one) is redone with larger buffers.
+namespace {
+
+struct BinPlan {
+    int64_t mCap = 0;
+    int lenCap = 0;
+};
+std::mutex gPlanMutex;
+BinPlan gPlans[64];
+
+BinPlan getPlan(int dev) {
+    std::lock_guard<std::mutex> lock(gPlanMutex);
+    return gPlans[dev & 63];
+}
+
+void growPlan(int dev, int m, int maxLen) {
+    std::lock_guard<std::mutex> lock(gPlanMutex);
+    BinPlan &p = gPlans[dev & 63];
+    if (m > p.mCap) p.mCap = (int64_t)m + m / 4 + 4096;
+    if (maxLen > p.lenCap) {
+        const int64_t want = (int64_t)maxLen + maxLen / 4;
+        int64_t cap = 64;
+        while (cap < want) cap <<= 1;
+        if (cap > 64 && cap < 256) cap = 256;
+        p.lenCap = (int)std::min<int64_t>(cap, gsb_bucket_max_tile_len());
+    }
+}
+
+// pinned landing buffer of the stats read-back, one per (thread, device)
+torch::Tensor &statsHostFor(int dev) {
+    static thread_local torch::Tensor bufs[64];
+    torch::Tensor &b = bufs[dev & 63];
+    if (!b.defined()) b = torch::zeros({4}, torch::TensorOptions().dtype(torch::kInt32).pinned_memory(true));
+    return b;
+}
+
+inline char *align256(torch::Tensor &t) {
+    char *p = (char *)t.data_ptr();
+    return p + (256 - ((uintptr_t)p % 256)) % 256;
+}
+
+}  // namespace
+
 torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xys, torch::Tensor depths,
                                           torch::Tensor radii, torch::Tensor conics, torch::Tensor numTilesHit,
                                           torch::Tensor colors, torch::Tensor opacity, int imgHeight,
@@ -61,71 +113,87 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
     const int n = (int)xys.size(0);
     TORCH_CHECK(colors.size(-1) == 3, "RasterizeGaussians: only 3 colour channels are supported");
     c10::cuda::CUDAGuard guard(xys.device());
+    const int dev = xys.device().index();
     const TileBounds tileBounds =
         std::make_tuple((imgWidth + BLOCK_X - 1) / BLOCK_X, (imgHeight + BLOCK_Y - 1) / BLOCK_Y, 1);
     const int tilesX = std::get<0>(tileBounds), tilesY = std::get<1>(tileBounds);
-    torch::Tensor x = gsb::f32(xys), con = gsb::f32(conics), col = gsb::f32(colors), op = gsb::f32(opacity);
-    torch::Tensor bg = gsb::f32(background), nth = gsb::i32(numTilesHit);
-
-    // inclusive scan (slot offsets of the gradient rows) ...
-    torch::Tensor cum = torch::empty({n}, gsb::like(x, torch::kInt32));
-    torch::Tensor d = gsb::f32(depths), r = gsb::i32(radii);
     const int numTiles = tilesX * tilesY;
+    torch::Tensor x = gsb::f32(xys), con = gsb::f32(conics), col = gsb::f32(colors), op = gsb::f32(opacity);
+    torch::Tensor bg = gsb::f32(background), d = gsb::f32(depths), r = gsb::i32(radii);
+
+    torch::Tensor cum = torch::empty({n}, gsb::like(x, torch::kInt32));
     torch::Tensor tileBins = torch::empty({numTiles, 2}, gsb::like(x, torch::kInt32));
-    torch::Tensor stats = torch::zeros({2}, gsb::like(x, torch::kInt32));
-    torch::Tensor tileCursor = torch::empty({(int64_t)gsb_bucket_cursor_bytes(numTiles) / 4}, gsb::like(x, torch::kInt32));
-    if (n > 0) {
+    torch::Tensor stats = torch::empty({4}, gsb::like(x, torch::kInt32));
+    torch::Tensor outImg = torch::empty({imgHeight, imgWidth, 3}, gsb::like(x, torch::kFloat32));
+    torch::Tensor finalTs = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kFloat32));
+    torch::Tensor finalIdx = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kInt32));
+    torch::Tensor records;
+    torch::Tensor &statsHost = statsHostFor(dev);
+    const int limit = gsb_bucket_max_tile_len();
+    int mRaster = 0;   // what the records buffer is sized with (the blend kernels' scratch words sit behind it)
+    const int cull = 1;
+    while (true) {
+        const BinPlan plan = getPlan(dev);
+        const int mCap = (int)std::min<int64_t>(plan.mCap, INT32_MAX - 1024), lenCap = plan.lenCap;
+        const size_t wsBytes = gsb_bucket_workspace_bytes(n, mCap, numTiles);
+        torch::Tensor ws = torch::empty({(int64_t)wsBytes + 256}, gsb::like(x, torch::kUInt8));
+        char *wp = align256(ws);
+        records = torch::empty({(int64_t)gsb_raster_records_bytes(mCap)}, gsb::like(x, torch::kUInt8));
+        gsb::check(gsb_bucket_tile_ranges(n, gsb::fp(x), r.data_ptr<int32_t>(), gsb::fp(con), gsb::fp(col),
+                                          gsb::fp(op), cull, tilesX, tilesY, mCap, lenCap, wp, wsBytes,
+                                          cum.data_ptr<int32_t>(), tileBins.data_ptr<int32_t>(),
+                                          stats.data_ptr<int32_t>(), gsb::stream()),
+                   "gsb_bucket_tile_ranges");
+        statsHost.copy_(stats, /*non_blocking=*/true);
+        at::cuda::CUDAEvent statsReady;
+        statsReady.record(c10::cuda::getCurrentCUDAStream());
+        if (mCap > 0)
+            gsb::check(gsb_bucket_sort_pack(n, mCap, lenCap, gsb::fp(d), r.data_ptr<int32_t>(),
+                                            cum.data_ptr<int32_t>(), cull, tilesX, tilesY,
+                                            tileBins.data_ptr<int32_t>(), stats.data_ptr<int32_t>(), wp, wsBytes,
+                                            records.data_ptr(), nullptr, nullptr, gsb::stream()),
+                       "gsb_bucket_sort_pack");
+        gsb::check(gsb_rasterize_forward_packed(imgHeight, imgWidth, tilesX, tilesY, mCap,
+                                                tileBins.data_ptr<int32_t>(), stats.data_ptr<int32_t>(), gsb::fp(bg),
+                                                records.data_ptr(), gsb::fpw(outImg), gsb::fpw(finalTs),
+                                                finalIdx.data_ptr<int32_t>(), gsb::stream()),
+                   "gsb_rasterize_forward_packed");
+        // the path's single device->host read-back (rasterize_gaussians.cpp:63), waited for with the GPU busy
+        statsReady.synchronize();
+        const int32_t *sh = statsHost.data_ptr<int32_t>();
+        const int m = sh[0], maxLen = sh[1];
+        const bool overflow = sh[2] != 0;
+        mRaster = mCap;
+        if (!overflow) break;
+        if (maxLen <= limit) {
+            growPlan(dev, m, maxLen);
+            continue;
+        }
+        // pathological tile lists: generic global radix sort on the reference's own (unculled) intersection lists
+        torch::Tensor nth = gsb::i32(numTilesHit);
         const size_t sb = gsb_cumsum_workspace_bytes(n);
         torch::Tensor sws = torch::empty({(int64_t)sb}, gsb::like(x, torch::kUInt8));
         gsb::check(gsb_cumsum_tiles_hit(n, nth.data_ptr<int32_t>(), cum.data_ptr<int32_t>(), sws.data_ptr(), sb,
                                         nullptr, gsb::stream()),
                    "gsb_cumsum_tiles_hit");
-    }
-    // ... tile sizes -> tile_bins, and the path's single device->host read-back (rasterize_gaussians.cpp:63):
-    // M together with the longest tile list
-    gsb::check(gsb_bucket_tile_ranges(n, gsb::fp(x), r.data_ptr<int32_t>(), tilesX, tilesY,
-                                      tileBins.data_ptr<int32_t>(), tileCursor.data_ptr<int32_t>(),
-                                      stats.data_ptr<int32_t>(), gsb::stream()),
-               "gsb_bucket_tile_ranges");
-    torch::Tensor statsHost = stats.cpu();
-    const int m = statsHost[0].item<int>(), maxLen = statsHost[1].item<int>();
-
-    torch::Tensor records = torch::empty({(int64_t)gsb_raster_records_bytes(m)}, gsb::like(x, torch::kUInt8));
-    torch::Tensor outImg = torch::empty({imgHeight, imgWidth, 3}, gsb::like(x, torch::kFloat32));
-    torch::Tensor finalTs = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kFloat32));
-    torch::Tensor finalIdx = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kInt32));
-    if (maxLen <= gsb_bucket_max_tile_len()) {
-        // fast path: two-level bucket sort fused with the record packing
-        const size_t wsBytes = gsb_bucket_workspace_bytes(n, m);
-        torch::Tensor ws = torch::empty({(int64_t)wsBytes + 256}, gsb::like(x, torch::kUInt8));
-        char *wp = (char *)ws.data_ptr();
-        wp += (256 - ((uintptr_t)wp % 256)) % 256;
-        gsb::check(gsb_bucket_sort_pack(n, m, maxLen, gsb::fp(x), gsb::fp(d), r.data_ptr<int32_t>(),
-                                        cum.data_ptr<int32_t>(), tilesX, tilesY, tileBins.data_ptr<int32_t>(),
-                                        tileCursor.data_ptr<int32_t>(), gsb::fp(con), gsb::fp(col), gsb::fp(op), wp, wsBytes, records.data_ptr(),
-                                        nullptr, nullptr, gsb::stream()),
-                   "gsb_bucket_sort_pack");
-        gsb::check(gsb_rasterize_forward_packed(imgHeight, imgWidth, tilesX, tilesY, m,
-                                                tileBins.data_ptr<int32_t>(), gsb::fp(bg), records.data_ptr(),
-                                                gsb::fpw(outImg), gsb::fpw(finalTs), finalIdx.data_ptr<int32_t>(),
-                                                gsb::stream()),
-                   "gsb_rasterize_forward_packed");
-    } else {
-        // pathological tile lists: generic global radix sort
-        Binned b = bin_and_sort(n, m, x, d, r, cum, tileBounds);
+        const int mRef = cum[n - 1].item<int>();
+        Binned b = bin_and_sort(n, mRef, x, d, r, cum, tileBounds);
         tileBins = b.tileBins;
-        gsb::check(gsb_rasterize_forward(imgHeight, imgWidth, tilesX, tilesY, m,
+        records = torch::empty({(int64_t)gsb_raster_records_bytes(mRef)}, gsb::like(x, torch::kUInt8));
+        gsb::check(gsb_rasterize_forward(imgHeight, imgWidth, tilesX, tilesY, mRef,
                                          b.gaussianIdsSorted.data_ptr<int32_t>(),
                                          b.sortedIndex.data_ptr<int32_t>(), b.tileBins.data_ptr<int32_t>(),
                                          gsb::fp(x), gsb::fp(con), gsb::fp(col), gsb::fp(op), gsb::fp(bg),
                                          records.data_ptr(), gsb::fpw(outImg), gsb::fpw(finalTs),
                                          finalIdx.data_ptr<int32_t>(), gsb::stream()),
                    "gsb_rasterize_forward");
+        mRaster = mRef;
+        break;
     }
 
     ctx->saved_data["imgWidth"] = imgWidth;
     ctx->saved_data["imgHeight"] = imgHeight;
-    ctx->saved_data["numIntersects"] = m;
+    ctx->saved_data["numIntersects"] = mRaster;
     ctx->save_for_backward({tileBins, con, op, records, cum, bg, finalTs, finalIdx});
     return outImg;
 }

@@ -105,7 +105,10 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
             my_max = max(my_max, binf[j]);
         }
         const int warp_max = __reduce_max_sync(0xffffffffu, my_max);
-        const int hi = min(range.y - 1, warp_max);  // last sorted index any pixel of this tile blended
+        // last sorted index any pixel of this tile blended, clamped into the tile's OWN segment: final_idx
+        // defaults to 0 for pixels that blended nothing (forward.cu:300), which is below range.x for every tile
+        // but the first -- without the clamp the zero-row loop below would walk over other tiles' rows.
+        const int hi = min(range.y - 1, max(warp_max, range.x - 1));
 
         // intersections behind every pixel's last contributor: zero rows
         for (int idx = hi + 1 + lane; idx < range.y; idx += 32)

@@ -71,16 +71,24 @@ __device__ __forceinline__ GsbRecord make_record(float2 xy, float a, float b, fl
     return rec;
 }
 
-// Per-lane cull of record `lane` of a chunk against this warp's tile: returns the 8-bit mask of slots
-// (row pairs) whose rows intersect the record's y-extent, or 0 if the record cannot touch the tile.
-__device__ __forceinline__ unsigned record_slot_mask(const GsbRecord &r, float tile_x0, float tile_y0) {
-    const float gx = r.q0.x - tile_x0, gy = r.q0.y - tile_y0;   // centre in tile-local pixel coords
-    const float hx = r.q1.w, hy = r.q2.w;
+// Slot mask of a Gaussian with centre (cx, cy) and extent half-widths (hx, hy) against the tile whose first
+// pixel is (tile_x0, tile_y0): the 8-bit mask of slots (row pairs) whose rows intersect the y-extent, or 0 if
+// the extent box misses the tile.  Only additions, comparisons and exact roundings -- no multiplications, so
+// every kernel that evaluates it on the same floats takes the same decision (the tile binning's cull and
+// the blend kernels' per-record test must agree).
+__device__ __forceinline__ unsigned extent_slot_mask(float cx, float cy, float hx, float hy, float tile_x0,
+                                                     float tile_y0) {
+    const float gx = cx - tile_x0, gy = cy - tile_y0;   // centre in tile-local pixel coords
     // pixel centres of the tile are 0..15 in both axes
     const bool hit_x = (gx + hx >= 0.f) && (gx - hx <= 15.f);
     const float ylo = fmaxf(ceilf(gy - hy), 0.f), yhi = fminf(floorf(gy + hy), 15.f);
     if (!hit_x || !(ylo <= yhi)) return 0u;
     const int jlo = (int)ylo >> 1, jhi = (int)yhi >> 1;
     return ((2u << jhi) - 1u) & ~((1u << jlo) - 1u);
+}
+
+// Per-lane cull of record `lane` of a chunk against this warp's tile.
+__device__ __forceinline__ unsigned record_slot_mask(const GsbRecord &r, float tile_x0, float tile_y0) {
+    return extent_slot_mask(r.q0.x, r.q0.y, r.q1.w, r.q2.w, tile_x0, tile_y0);
 }
 #endif

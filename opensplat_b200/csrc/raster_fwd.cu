@@ -56,7 +56,10 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                          const int2 *__restrict__ tile_bins, const GsbRecord *__restrict__ records,
                          const float *__restrict__ background, float *__restrict__ out_img,
                          float *__restrict__ final_Ts, int *__restrict__ final_idx,
-                         unsigned *__restrict__ tile_counter) {
+                         unsigned *__restrict__ tile_counter, const int *__restrict__ bin_stats) {
+    // bin_stats (optional): stats of gsb_bucket_tile_ranges; [2] != 0 means the binning overflowed its
+    // capacities and wrote nothing -- the host redoes the frame, this launch must not touch the records
+    if (bin_stats && bin_stats[2]) return;
     __shared__ WarpRing rings[RK_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpRing &ring = rings[warp];
@@ -249,15 +252,15 @@ extern "C" int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tile
     const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel, num_tiles);
     rasterize_forward_kernel<<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters);
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr);
     GSB_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, int tiles_y, int m,
-                                            const int32_t *tile_bins, const float *background,
-                                            void *records, float *out_img, float *final_Ts,
-                                            int32_t *final_idx, gsb_stream_t stream) {
+                                            const int32_t *tile_bins, const int32_t *bin_stats,
+                                            const float *background, void *records, float *out_img,
+                                            float *final_Ts, int32_t *final_idx, gsb_stream_t stream) {
     GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0);
     GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
     GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx && records);
@@ -270,7 +273,7 @@ extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, i
     const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel, num_tiles);
     rasterize_forward_kernel<<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters);
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, bin_stats);
     GSB_LAUNCH_CHECK();
     return 0;
 }
@@ -288,11 +291,22 @@ int gsb_sm_count() {
     return cached;
 }
 
-// persistent grid: SMs x resident CTAs per SM (never more CTAs than there are tile groups)
+// persistent grid: SMs x resident CTAs per SM (never more CTAs than there are tile groups).  The occupancy query
+// costs a few microseconds of host time per call, so its result is cached per (thread, device, kernel).
 int gsb_blend_grid(const void *kernel, int num_tiles) {
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RK_THREADS, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
+    struct Entry { const void *kernel; int dev; int per_sm; };
+    static thread_local Entry cache[4] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int per_sm = 0;
+    for (const Entry &e : cache)
+        if (e.kernel == kernel && e.dev == dev) per_sm = e.per_sm;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RK_THREADS, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        for (Entry &e : cache)
+            if (e.kernel == nullptr || e.kernel == kernel) { e = Entry{kernel, dev, per_sm}; break; }
+    }
     const int full = gsb_sm_count() * per_sm;
     const int need = gsb_div_up(num_tiles, RK_WARPS);
     return need < full ? need : full;

@@ -181,46 +181,105 @@ def binAndSortGaussians(numPoints, numIntersects, xys, depths, radii, cumTilesHi
     return isect, gids, ks, gs, bins
 
 
-def bucket_tile_ranges(xys, radii, tile_bounds_):
-    """Fast-path phase 1: tile_bins [T,2], the per-tile write cursors for phase 2, and
-    stats = (M, longest tile list), without sorting."""
+class BinPlan:
+    """Capacities of the M-dependent buffers of the fast binning path, carried from frame to frame (grow-only
+    high-water marks with headroom) so that a frame needs no host read-back before its kernels are enqueued:
+    the kernels are sized by these capacities, raise stats[2] if a frame outgrows them, and the host checks the
+    (asynchronous) read-back after enqueuing the whole forward pass.  One instance per device (operator layer) or
+    per pipeline."""
+
+    def __init__(self):
+        self.m_cap = 0
+        self.len_cap = 0
+        self.host = None   # pinned int32[4]
+        self.event = None
+
+    def grow(self, m, max_len):
+        if m > self.m_cap:
+            self.m_cap = int(m * 1.25) + 4096
+        if max_len > self.len_cap:
+            want = max_len + max_len // 4
+            cap = 64
+            while cap < want:
+                cap <<= 1
+            if cap > 64 and cap < 256:
+                cap = 256
+            # never plan beyond what the in-shared-memory sort can take; longer lists go the generic way
+            self.len_cap = min(cap, capi.lib().gsb_bucket_max_tile_len())
+
+    def read_back(self, stats):
+        """Enqueue the asynchronous D2H copy of the device stats; returns after recording the event."""
+        if self.host is None:
+            self.host = torch.zeros(4, dtype=torch.int32).pin_memory()
+            self.event = torch.cuda.Event()
+        self.host.copy_(stats, non_blocking=True)
+        self.event.record()
+
+    def wait(self):
+        self.event.synchronize()
+        m, max_len, overflow, _ = (int(v) for v in self.host.tolist())
+        return m, max_len, bool(overflow)
+
+
+_plans = {}
+
+
+def _plan_for(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    p = _plans.get(key)
+    if p is None:
+        p = _plans[key] = BinPlan()
+    return p
+
+
+def bucket_tile_ranges(xys, radii, conics, colors, opacities, tile_bounds_, m_capacity, len_capacity, cull=True,
+                       workspace=None):
+    """Fast-path phase 1: per-Gaussian attribute records (kept in the workspace), cum_tiles_hit [n], tile_bins
+    [T,2] and the device stats {M, longest tile list, overflow, 0}, without sorting and without a read-back."""
     n = xys.shape[0]
     T = tile_bounds_[0] * tile_bounds_[1]
-    bins = _empty((T, 2), torch.int32, xys)
-    cursor = torch.empty(capi.lib().gsb_bucket_cursor_bytes(T), dtype=torch.uint8, device=xys.device)
-    stats = _empty((2,), torch.int32, xys)
-    capi.check(capi.lib().gsb_bucket_tile_ranges(n, capi.ptr(capi.f32(xys)), capi.ptr(radii.contiguous()),
-                                                 tile_bounds_[0], tile_bounds_[1], capi.ptr(bins), capi.ptr(cursor),
-                                                 capi.ptr(stats), capi.stream()))
-    return bins, cursor, stats
-
-
-def bucket_sort_pack(n, m, max_tile_len, xys, depths, radii, cum_tiles_hit, tile_bounds_, tile_bins, tile_cursor,
-                     conics, colors, opacities, want_index=False):
-    """Fast-path phase 2: bucket emit + per-tile shared-memory sort + record pack -> records (+ optional
-    sorted_index / gaussian_ids_sorted for inspection).  Consumes tile_cursor."""
     L = capi.lib()
-    ws = _ws.get(xys.device, "bucket", L.gsb_bucket_workspace_bytes(n, m) + 256)
-    off = (-ws.data_ptr()) % 256
-    records = torch.empty(L.gsb_raster_records_bytes(m), dtype=torch.uint8, device=xys.device)
-    idx = _empty((m,), torch.int32, xys) if want_index else None
-    gs = _empty((m,), torch.int32, xys) if want_index else None
+    if workspace is None:
+        workspace = torch.empty(L.gsb_bucket_workspace_bytes(n, m_capacity, T) + 256, dtype=torch.uint8,
+                                device=xys.device)
+    off = (-workspace.data_ptr()) % 256
+    bins = _empty((T, 2), torch.int32, xys)
+    cum = _empty((n,), torch.int32, xys)
+    stats = _empty((4,), torch.int32, xys)
+    capi.check(L.gsb_bucket_tile_ranges(
+        n, capi.ptr(capi.f32(xys)), capi.ptr(radii.contiguous()), capi.ptr(capi.f32(conics)),
+        capi.ptr(capi.f32(colors)), capi.ptr(capi.f32(opacities)), 1 if cull else 0, tile_bounds_[0],
+        tile_bounds_[1], m_capacity, len_capacity, workspace.data_ptr() + off, workspace.numel() - off,
+        capi.ptr(cum), capi.ptr(bins), capi.ptr(stats), capi.stream()))
+    return bins, cum, stats, workspace
+
+
+def bucket_sort_pack(n, m_capacity, len_capacity, depths, radii, cum_tiles_hit, tile_bounds_, tile_bins, stats,
+                     workspace, cull=True, want_index=False):
+    """Fast-path phase 2: bucket emit + per-tile shared-memory sort + record pack -> records (+ optional
+    sorted_index / gaussian_ids_sorted for inspection), sized by the capacities phase 1 was given."""
+    L = capi.lib()
+    off = (-workspace.data_ptr()) % 256
+    records = torch.empty(L.gsb_raster_records_bytes(m_capacity), dtype=torch.uint8, device=depths.device)
+    idx = _empty((m_capacity,), torch.int32, depths) if want_index else None
+    gs = _empty((m_capacity,), torch.int32, depths) if want_index else None
     capi.check(L.gsb_bucket_sort_pack(
-        n, m, max_tile_len, capi.ptr(capi.f32(xys)), capi.ptr(capi.f32(depths)), capi.ptr(radii.contiguous()),
-        capi.ptr(cum_tiles_hit), tile_bounds_[0], tile_bounds_[1], capi.ptr(tile_bins), capi.ptr(tile_cursor),
-        capi.ptr(capi.f32(conics)), capi.ptr(capi.f32(colors)), capi.ptr(capi.f32(opacities)), ws.data_ptr() + off,
-        ws.numel() - off, capi.ptr(records), capi.ptr(idx), capi.ptr(gs), capi.stream()))
+        n, m_capacity, len_capacity, capi.ptr(capi.f32(depths)), capi.ptr(radii.contiguous()),
+        capi.ptr(cum_tiles_hit), 1 if cull else 0, tile_bounds_[0], tile_bounds_[1], capi.ptr(tile_bins),
+        capi.ptr(stats), workspace.data_ptr() + off, workspace.numel() - off, capi.ptr(records), capi.ptr(idx),
+        capi.ptr(gs), capi.stream()))
     return records, idx, gs
 
 
-def rasterize_forward_packed(tile_bounds_, img_size, m, tile_bins, records, background):
+def rasterize_forward_packed(tile_bounds_, img_size, m_capacity, tile_bins, records, background, stats=None):
     W, H = img_size[0], img_size[1]
     out = _empty((H, W, 3), torch.float32, records)
     fT = _empty((H, W), torch.float32, records)
     fI = _empty((H, W), torch.int32, records)
     capi.check(capi.lib().gsb_rasterize_forward_packed(
-        H, W, tile_bounds_[0], tile_bounds_[1], m, capi.ptr(tile_bins), capi.ptr(capi.f32(background)),
-        capi.ptr(records), capi.ptr(out), capi.ptr(fT), capi.ptr(fI), capi.stream()))
+        H, W, tile_bounds_[0], tile_bounds_[1], m_capacity, capi.ptr(tile_bins), capi.ptr(stats),
+        capi.ptr(capi.f32(background)), capi.ptr(records), capi.ptr(out), capi.ptr(fT), capi.ptr(fI),
+        capi.stream()))
     return out, fT, fI
 
 
@@ -301,21 +360,39 @@ class RasterizeGaussians(torch.autograd.Function):
         tb = tile_bounds(imgWidth, imgHeight)
         if colors.shape[-1] != 3:
             raise ValueError("only 3-channel colors are supported")
-        cum = cumsum_tiles_hit(numTilesHit)
-        bins, cursor, stats = bucket_tile_ranges(xys, radii, tb)
-        # the one device->host read-back of the path (rasterize_gaussians.cpp:63): M and the longest tile list
-        numIntersects, max_len = (int(v) for v in stats.tolist())
-        if max_len <= capi.lib().gsb_bucket_max_tile_len():
-            records, _, _ = bucket_sort_pack(numPoints, numIntersects, max_len, xys, depths, radii, cum, tb, bins,
-                                             cursor, conics, colors, opacity)
-            out, fT, fI = rasterize_forward_packed(tb, (imgWidth, imgHeight, 1), numIntersects, bins, records,
-                                                   background)
-        else:  # pathological tile lists: generic global radix sort (binAndSortGaussians)
-            _, _, _, gs, bins, idx = binAndSortGaussians(numPoints, numIntersects, xys, depths, radii, cum, tb,
+        limit = capi.lib().gsb_bucket_max_tile_len()
+        plan = _plan_for(xys.device)
+        # Binning, packing and blending are enqueued with buffer capacities planned from earlier frames; the one
+        # device->host read-back of the path (M, rasterize_gaussians.cpp:63) is waited for only AFTER the whole
+        # forward pass has been enqueued, and a frame that outgrew the plan (or the first one) is simply redone.
+        while True:
+            m_cap, len_cap = plan.m_cap, plan.len_cap
+            bins, cum, stats, ws = bucket_tile_ranges(xys, radii, conics, colors, opacity, tb, m_cap, len_cap)
+            plan.read_back(stats)
+            if m_cap > 0:
+                records, _, _ = bucket_sort_pack(numPoints, m_cap, len_cap, depths, radii, cum, tb, bins, stats, ws)
+                out, fT, fI = rasterize_forward_packed(tb, (imgWidth, imgHeight, 1), m_cap, bins, records,
+                                                       background, stats)
+            numIntersects, max_len, overflow = plan.wait()
+            if not overflow:
+                if m_cap == 0:   # no plan yet and nothing on screen: background only
+                    records = torch.empty(capi.lib().gsb_raster_records_bytes(0), dtype=torch.uint8,
+                                          device=xys.device)
+                    out, fT, fI = rasterize_forward_packed(tb, (imgWidth, imgHeight, 1), 0, bins, records, background)
+                break
+            if max_len <= limit:
+                plan.grow(numIntersects, max_len)
+                continue
+            # pathological tile lists (longer than the in-shared-memory sort can take): generic global radix
+            # sort (binAndSortGaussians) on the reference's own, unculled intersection lists
+            cum = cumsum_tiles_hit(numTilesHit)
+            m_cap = int(cum[-1])
+            _, _, _, gs, bins, idx = binAndSortGaussians(numPoints, m_cap, xys, depths, radii, cum, tb,
                                                          return_index=True)
             out, fT, fI, records = rasterize_forward(tb, (imgWidth, imgHeight, 1), gs, idx, bins, xys, conics,
                                                      colors, opacity, background)
-        ctx.meta = (int(imgHeight), int(imgWidth), numPoints, numIntersects)
+            break
+        ctx.meta = (int(imgHeight), int(imgWidth), numPoints, m_cap)
         ctx.save_for_backward(bins, conics, opacity, records, cum, background, fT, fI)
         return out
 

@@ -7,8 +7,10 @@ import torch
 import torch.distributed as dist
 
 
-def flat_layout(n, sh_bases):
-    """Per-tensor (name, shape) list and element offsets of the flat parameter / gradient buffer."""
+def flat_layout(n, sh_bases, align=4):
+    """Per-tensor (offset, count, shape) of the flat parameter / gradient buffer and its total length (floats).
+    Every slice starts on a multiple of `align` floats (16 bytes), whatever n is: the projection kernels use
+    128-bit accesses on the quaternion slices, and a refinement may leave an odd Gaussian count."""
     sizes = [("means", (n, 3)), ("scales", (n, 3)), ("quats", (n, 4)), ("opacities", (n, 1)),
              ("coeffs", (n, sh_bases, 3))]
     offs, o = {}, 0
@@ -17,7 +19,7 @@ def flat_layout(n, sh_bases):
         for d in shp:
             c *= d
         offs[name] = (o, c, shp)
-        o += c
+        o += (c + align - 1) // align * align
     return offs, o
 
 

@@ -15,7 +15,8 @@ import os
 import torch
 
 from . import capi
-from .ops import tile_bounds, num_sh_bases
+from .ops import tile_bounds, num_sh_bases, BinPlan
+from .parallel import flat_layout
 
 
 class SplatPipeline:
@@ -39,16 +40,18 @@ class SplatPipeline:
         self.background = torch.zeros(3, dtype=f32, device=d)
         self.loss = torch.zeros(1, dtype=f32, device=d)
         self.tile_bins = torch.empty((self.T, 2), dtype=i32, device=d)
-        self.tile_cursor = torch.empty(self.L.gsb_bucket_cursor_bytes(self.T), dtype=torch.uint8, device=d)
+        self.stats_dev = torch.zeros(4, dtype=i32, device=d)
+        self.plan = BinPlan()   # capacities of the M-dependent buffers, carried from frame to frame
+        self.cull = True        # bin only (Gaussian, tile) pairs whose extent box touches the tile
         # ---- camera ----
         self.viewmat = torch.eye(4, dtype=f32, device=d)
         self.projmat = torch.eye(4, dtype=f32, device=d)
         self.intr = (1.0, 1.0, 0.0, 0.0)
         # ---- M-dependent (grown on demand) ----
-        self.m_cap = 0
         self.m = 0
+        self.m_raster = 0
         if m_capacity:
-            self._grow(int(m_capacity))
+            self.plan.grow(int(m_capacity), 0)
         self.nvtx = os.environ.get("GSB_NVTX", "0") == "1"
         self._nvtx_open = False
         self.exchange = None  # multigpu.ViewParallelExchange (fused SH backward + NVLink exchange)
@@ -63,19 +66,18 @@ class SplatPipeline:
         refinement changed the count (resize_gaussians)."""
         self.n = n = int(n)
         d, f32, i32 = self.dev, torch.float32, torch.int32
-        # ---- parameters: one flat buffer, views per tensor (same layout for grads / Adam state) ----
-        self.sizes = [("means", (n, 3)), ("scales", (n, 3)), ("quats", (n, 4)), ("opacities", (n, 1)),
-                      ("coeffs", (n, self.K, 3))]
-        self.numel = sum(int(torch.Size(s).numel()) for _, s in self.sizes)
+        # ---- parameters: one flat buffer, views per tensor (same layout for grads / Adam state); every slice
+        # starts on a 16-byte boundary (parallel.flat_layout) whatever n is, so the 128-bit accesses of the
+        # projection kernels stay legal after a refinement left an odd Gaussian count
+        self.offs, self.numel = flat_layout(n, self.K)
+        self.sizes = [(name, shp) for name, (o, c, shp) in self.offs.items()]
+        self.geom_numel = self.offs["coeffs"][0]   # means, scales, quats, opacities: the prefix before the SH block
         self.param_flat = torch.zeros(self.numel, dtype=f32, device=d)
-        self.grad_flat = torch.zeros(self.numel, dtype=f32, device=d)
+        self.grad_flat = self._alloc_grad_flat(self.numel)
         self.p, self.g = {}, {}
-        o = 0
-        for name, shp in self.sizes:
-            c = int(torch.Size(shp).numel())
+        for name, (o, c, shp) in self.offs.items():
             self.p[name] = self.param_flat[o:o + c].view(shp)
             self.g[name] = self.grad_flat[o:o + c].view(shp)
-            o += c
         self.adam_m = self.adam_v = None
         self.adam_t = 0
         # ---- per-Gaussian intermediates ----
@@ -94,13 +96,33 @@ class SplatPipeline:
         self.v_rgbs = torch.empty((n, 3), dtype=f32, device=d)
         self.scan_ws = torch.empty(self.L.gsb_cumsum_workspace_bytes(n), dtype=torch.uint8, device=d)
         self.total_dev = torch.zeros(2, dtype=i32, device=d)
-        self.total_host = torch.zeros(2, dtype=i32).pin_memory()
         self.max_len = 0
-        self._m_event = torch.cuda.Event()
-        self.m_cap = 0   # bucket workspace depends on n: regrown on the next forward
+        self.m_cap = -1   # the M-sized buffers (and the n-sized bucket workspace) are (re)built by the next forward
+        self._generic_cap = 0
+
+    def _alloc_grad_flat(self, numel):
+        """The flat gradient buffer; multigpu.ViewParallelExchange re-binds it to symmetric (peer-mapped) memory."""
+        return torch.zeros(numel, dtype=torch.float32, device=self.dev)
+
+    def rebind_grad_flat(self, flat):
+        """Adopt `flat` (same numel; e.g. a symmetric-memory tensor) as the gradient buffer."""
+        assert flat.numel() == self.numel and flat.dtype == torch.float32
+        self.grad_flat = flat
+        for name, (o, c, shp) in self.offs.items():
+            self.g[name] = self.grad_flat[o:o + c].view(shp)
 
     # ------------------------------------------------------------------------------------------
-    def _grow(self, m):
+    def _grow(self, m_cap):
+        """(Re)allocates the buffers sized by the intersection capacity of the fast path."""
+        d = self.dev
+        self.records = torch.empty(self.L.gsb_raster_records_bytes(m_cap), dtype=torch.uint8, device=d)
+        self.grad_rows = torch.empty(self.L.gsb_raster_grad_rows_bytes(m_cap), dtype=torch.uint8, device=d)
+        self.bucket_ws = torch.empty(self.L.gsb_bucket_workspace_bytes(self.n, m_cap, self.T) + 256,
+                                     dtype=torch.uint8, device=d)
+        self.m_cap = m_cap
+
+    def _grow_generic(self, m):
+        """Buffers of the generic (global radix sort) path, allocated only when it is taken."""
         cap = int(m * 1.25) + 1024
         d = self.dev
         self.isect = torch.empty(cap, dtype=torch.int64, device=d)
@@ -109,10 +131,7 @@ class SplatPipeline:
         self.sorted_index = torch.empty(cap, dtype=torch.int32, device=d)
         self.gids_sorted = torch.empty(cap, dtype=torch.int32, device=d)
         self.sort_ws = torch.empty(self.L.gsb_sort_workspace_bytes(cap) + 256, dtype=torch.uint8, device=d)
-        self.records = torch.empty(self.L.gsb_raster_records_bytes(cap), dtype=torch.uint8, device=d)
-        self.grad_rows = torch.empty(self.L.gsb_raster_grad_rows_bytes(cap), dtype=torch.uint8, device=d)
-        self.bucket_ws = torch.empty(self.L.gsb_bucket_workspace_bytes(self.n, cap) + 256, dtype=torch.uint8, device=d)
-        self.m_cap = cap
+        self._generic_cap = cap
 
     def load_scene(self, sc):
         """sc: dict from opensplat_b200.scene.make_scene (numpy)."""
@@ -159,70 +178,84 @@ class SplatPipeline:
         n, W, H = self.n, self.W, self.H
         fx, fy, cx, cy = self.intr
         p = self.p
+        self._stage("sh_fwd")
+        # SH colour with the glue of model.cpp:192 fused: rgbs = clamp_min(colors + 0.5, 0)
+        capi.check(L.gsb_sh_forward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(p["coeffs"]), 0.5, P(self.rgbs), s))
         self._stage("project_fwd")
         capi.check(L.gsb_project_forward(n, P(p["means"]), P(p["scales"]), 1.0, P(p["quats"]), P(self.viewmat),
                                          P(self.projmat), fx, fy, cx, cy, H, W, self.tb[0], self.tb[1], 0.01,
                                          P(self.cov3d), P(self.xys), P(self.depths), P(self.radii), P(self.conics),
                                          P(self.nth), s))
+        if self.binning == "bucket":
+            limit = L.gsb_bucket_max_tile_len()
+            plan = self.plan
+            cull = 1 if self.cull else 0
+            # Everything below is sized by capacities planned from earlier frames and enqueued WITHOUT waiting for
+            # the path's one device->host read-back (M, rasterize_gaussians.cpp:63): the host looks at it after
+            # the blend kernel has been enqueued (the GPU never idles) and redoes a frame that outgrew the plan.
+            while True:
+                if plan.m_cap != self.m_cap:
+                    self._grow(plan.m_cap)
+                m_cap, len_cap = plan.m_cap, plan.len_cap
+                boff = (-self.bucket_ws.data_ptr()) % 256
+                wsp, wsb = self.bucket_ws.data_ptr() + boff, self.bucket_ws.numel() - boff
+                self._stage("scan")
+                capi.check(L.gsb_bucket_tile_ranges(n, P(self.xys), P(self.radii), P(self.conics), P(self.rgbs),
+                                                    P(p["opacities"]), cull, self.tb[0], self.tb[1], m_cap, len_cap,
+                                                    wsp, wsb, P(self.cum), P(self.tile_bins), P(self.stats_dev), s))
+                plan.read_back(self.stats_dev)
+                if m_cap > 0:
+                    self._stage("bucket_sort_pack")
+                    capi.check(L.gsb_bucket_sort_pack(n, m_cap, len_cap, P(self.depths), P(self.radii), P(self.cum),
+                                                      cull, self.tb[0], self.tb[1], P(self.tile_bins),
+                                                      P(self.stats_dev), wsp, wsb, P(self.records), None, None, s))
+                self._stage("raster_fwd")
+                capi.check(L.gsb_rasterize_forward_packed(H, W, self.tb[0], self.tb[1], m_cap, P(self.tile_bins),
+                                                          P(self.stats_dev), P(self.background), P(self.records),
+                                                          P(self.out_img), P(self.final_Ts), P(self.final_idx), s))
+                self._stage("end_fwd")
+                self.m, self.max_len, overflow = plan.wait()
+                if not overflow:
+                    self.m_raster = m_cap
+                    return self.out_img
+                self._ev = []            # the frame is redone: drop its stage events
+                if self.max_len > limit:
+                    break                # pathological tile lists: generic path below
+                plan.grow(self.m, self.max_len)
+        # ---- generic path: reference-exact global sort (binAndSortGaussians), with the M read-back in the middle
         self._stage("scan")
         capi.check(L.gsb_cumsum_tiles_hit(n, P(self.nth), P(self.cum), P(self.scan_ws), self.scan_ws.numel(),
                                           P(self.total_dev), s))
-        use_bucket = self.binning == "bucket"
-        if use_bucket:
-            capi.check(L.gsb_bucket_tile_ranges(n, P(self.xys), P(self.radii), self.tb[0], self.tb[1],
-                                                P(self.tile_bins), P(self.tile_cursor), P(self.total_dev), s))
-        # the path's one device->host read-back (rasterize_gaussians.cpp:63): M (+ longest tile list).
-        # The host waits on an EVENT recorded right after the copy, and the SH colour pass (independent of the
-        # binning) is enqueued behind it: the GPU stays busy while the host wakes up and enqueues the rest.
-        self.total_host.copy_(self.total_dev, non_blocking=True)
-        self._m_event.record()
-        self._stage("sh_fwd")
-        # SH colour with the glue of model.cpp:192 fused: rgbs = clamp_min(colors + 0.5, 0)
-        capi.check(L.gsb_sh_forward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(p["coeffs"]), 0.5, P(self.rgbs), s))
-        self._m_event.synchronize()
-        m = int(self.total_host[0])
-        self.max_len = int(self.total_host[1]) if use_bucket else 0
-        self.m = m
-        if m > self.m_cap:
-            self._grow(m)
-        if use_bucket and self.max_len > L.gsb_bucket_max_tile_len():
-            use_bucket = False
-        if use_bucket:
-            self._stage("bucket_sort_pack")
-            boff = (-self.bucket_ws.data_ptr()) % 256
-            capi.check(L.gsb_bucket_sort_pack(n, m, self.max_len, P(self.xys), P(self.depths), P(self.radii),
-                                              P(self.cum), self.tb[0], self.tb[1], P(self.tile_bins),
-                                              P(self.tile_cursor), P(self.conics), P(self.rgbs), P(p["opacities"]),
-                                              self.bucket_ws.data_ptr() + boff,
-                                              self.bucket_ws.numel() - boff, P(self.records), None, None, s))
-            self._stage("raster_fwd")
-            capi.check(L.gsb_rasterize_forward_packed(H, W, self.tb[0], self.tb[1], m, P(self.tile_bins),
-                                                      P(self.background), P(self.records), P(self.out_img),
-                                                      P(self.final_Ts), P(self.final_idx), s))
-        else:
-            self._stage("emit")
-            capi.check(L.gsb_map_gaussian_to_intersects(n, m, P(self.xys), P(self.depths), P(self.radii),
-                                                        P(self.cum), self.tb[0], self.tb[1], P(self.isect),
-                                                        P(self.gids), s))
-            self._stage("sort")
-            off = (-self.sort_ws.data_ptr()) % 256
-            capi.check(L.gsb_sort_intersects(m, self.T, P(self.isect), P(self.isect_sorted), P(self.sorted_index),
-                                             self.sort_ws.data_ptr() + off, self.sort_ws.numel() - off, s))
-            self._stage("bins")
-            capi.check(L.gsb_gather_bin_edges(m, self.T, P(self.isect_sorted), P(self.sorted_index), P(self.gids),
-                                              P(self.gids_sorted), P(self.tile_bins), s))
-            self._stage("raster_fwd")
-            capi.check(L.gsb_rasterize_forward(H, W, self.tb[0], self.tb[1], m, P(self.gids_sorted),
-                                               P(self.sorted_index), P(self.tile_bins), P(self.xys), P(self.conics),
-                                               P(self.rgbs), P(p["opacities"]), P(self.background), P(self.records),
-                                               P(self.out_img), P(self.final_Ts), P(self.final_idx), s))
+        m = self.m = int(self.total_dev[0])
+        if m > self._generic_cap:
+            self._grow_generic(m)
+        if self.m_cap < 0 or self.L.gsb_raster_records_bytes(m) > self.records.numel():
+            self._grow(int(m * 1.25) + 1024)
+            self.plan.m_cap = self.m_cap
+        self._stage("emit")
+        capi.check(L.gsb_map_gaussian_to_intersects(n, m, P(self.xys), P(self.depths), P(self.radii),
+                                                    P(self.cum), self.tb[0], self.tb[1], P(self.isect),
+                                                    P(self.gids), s))
+        self._stage("sort")
+        off = (-self.sort_ws.data_ptr()) % 256
+        capi.check(L.gsb_sort_intersects(m, self.T, P(self.isect), P(self.isect_sorted), P(self.sorted_index),
+                                         self.sort_ws.data_ptr() + off, self.sort_ws.numel() - off, s))
+        self._stage("bins")
+        capi.check(L.gsb_gather_bin_edges(m, self.T, P(self.isect_sorted), P(self.sorted_index), P(self.gids),
+                                          P(self.gids_sorted), P(self.tile_bins), s))
+        self._stage("raster_fwd")
+        capi.check(L.gsb_rasterize_forward(H, W, self.tb[0], self.tb[1], m, P(self.gids_sorted),
+                                           P(self.sorted_index), P(self.tile_bins), P(self.xys), P(self.conics),
+                                           P(self.rgbs), P(p["opacities"]), P(self.background), P(self.records),
+                                           P(self.out_img), P(self.final_Ts), P(self.final_idx), s))
+        self.m_raster = m
         self._stage("end_fwd")
         return self.out_img
 
     def backward(self):
         """MSE loss against self.target + the whole backward path; grads land in self.grad_flat."""
         L, P, s = self.L, capi.ptr, capi.stream()
-        n, W, H, m = self.n, self.W, self.H, self.m
+        n, W, H, m = self.n, self.W, self.H, self.m_raster   # m: what the records buffer was sized with
         fx, fy, cx, cy = self.intr
         p, g = self.p, self.g
         cnt = H * W * 3
@@ -289,14 +322,11 @@ class SplatPipeline:
         for k in self.p:
             self.p[k].copy_(params[k].view(self.p[k].shape))
         if adam_m is not None and adam_v is not None:
-            self.adam_m = torch.empty_like(self.param_flat)
-            self.adam_v = torch.empty_like(self.param_flat)
-            o = 0
-            for name, shp in self.sizes:
-                c = int(torch.Size(shp).numel())
+            self.adam_m = torch.zeros_like(self.param_flat)
+            self.adam_v = torch.zeros_like(self.param_flat)
+            for name, (o, c, shp) in self.offs.items():
                 self.adam_m[o:o + c].copy_(adam_m[name].reshape(-1))
                 self.adam_v[o:o + c].copy_(adam_v[name].reshape(-1))
-                o += c
         if self.exchange is not None:
             self.exchange.resize(self)
 

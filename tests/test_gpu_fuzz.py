@@ -36,19 +36,24 @@ def test_random_configs_bucket_equals_generic(seed):
     colors = cu(rng.uniform(0, 1, (n, 3)).astype(np.float32))
     opac = cu(sc["opacities"])
     bg = cu(rng.uniform(0, 1, 3).astype(np.float32))
-    bins_b, cursor, stats = ops.bucket_tile_ranges(xys, radii, tb)
-    m, max_len = (int(v) for v in stats.tolist())
+    _, _, stats0, _ = ops.bucket_tile_ranges(xys, radii, conics, colors, opac, tb, 0, 0, cull=False)
+    m, max_len = (int(v) for v in stats0.tolist()[:2])
     assert m == (int(cum[-1]) if n else 0)
+    bins_b, cum_b, stats, ws = ops.bucket_tile_ranges(xys, radii, conics, colors, opac, tb, m, max_len, cull=False)
+    assert torch.equal(cum_b, cum)
     isect, gids, ks, gs, bins, idx = ops.binAndSortGaussians(n, m, xys, depths, radii, cum, tb, return_index=True)
     assert torch.equal(bins_b, bins)
     out, fT, fI, rec = ops.rasterize_forward(tb, (W, H, 1), gs, idx, bins, xys, conics, colors, opac, bg)
     if max_len <= 16384:
-        rec_b, idx_b, gs_b = ops.bucket_sort_pack(n, m, max_len, xys, depths, radii, cum, tb, bins_b, cursor, conics,
-                                                  colors, opac, want_index=True)
+        rec_b, idx_b, gs_b = ops.bucket_sort_pack(n, m, max_len, depths, radii, cum_b, tb, bins_b, stats, ws,
+                                                  cull=False, want_index=True)
         assert torch.equal(idx_b, idx) and torch.equal(gs_b, gs)
         assert torch.equal(rec_b[: m * 48], rec[: m * 48])
-        out_b, fT_b, fI_b = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins_b, rec_b, bg)
+        out_b, fT_b, fI_b = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins_b, rec_b, bg, stats)
         assert torch.equal(out, out_b) and torch.equal(fT, fT_b) and torch.equal(fI, fI_b)
+        # the operator (culled fast path, planned capacities, deferred read-back) renders the same image
+        img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, colors, opac, H, W, bg)
+        assert torch.equal(img, out)
     assert bool(torch.isfinite(out).all())
     v_out = cu(rng.uniform(-1, 1, (H, W, 3)).astype(np.float32))
     g1 = ops.rasterize_backward(H, W, n, m, bins, conics, opac, rec, cum, bg, fT, fI, v_out)

@@ -125,12 +125,26 @@ def test_binning_bit_exact(n, W, H, scale):
     assert np.array_equal(npy(bins), ob["tile_bins"])
 
 
+def _bucket_exact(xys, depths, radii, conics, colors, opac, tb, cull, want_index=True):
+    """Two-phase fast path with exact capacities (phase 1 once with zero capacities to learn M / longest list)."""
+    n = xys.shape[0]
+    _, _, stats0, _ = ops.bucket_tile_ranges(xys, radii, conics, colors, opac, tb, 0, 0, cull=cull)
+    m, max_len, ovf, _ = (int(v) for v in stats0.tolist())
+    assert ovf == (1 if m > 0 else 0)
+    bins, cum, stats, ws = ops.bucket_tile_ranges(xys, radii, conics, colors, opac, tb, m, max_len, cull=cull)
+    assert [int(v) for v in stats.tolist()] == [m, max_len, 0, 0]
+    rec, idx, gs = ops.bucket_sort_pack(n, m, max_len, depths, radii, cum, tb, bins, stats, ws, cull=cull,
+                                        want_index=want_index)
+    return m, max_len, bins, cum, stats, rec, idx, gs
+
+
 @pytest.mark.parametrize("n,W,H,scale", [(4000, 256, 256, 0.3), (30000, 640, 360, 0.15), (50, 48, 40, 2.0),
-                                         (200_000, 1024, 576, 0.05)])
+                                         (200_000, 1024, 576, 0.05), (1_000_000, 1920, 1080, 0.02)])
 def test_bucket_binning_matches_generic_sort(n, W, H, scale):
-    """The two-level fast path (tile bucket + in-smem depth sort + fused pack) must give the same tile_bins
-    and the same per-tile order as emit + global 64-bit sort + bin edges (bit-exact), and the same records."""
-    sc = _scene(n, W, H, scale, seed=3 * n)
+    """The two-level fast path (tile bucket + in-smem depth sort + fused pack), WITHOUT culling, must give the same
+    cum_tiles_hit, tile_bins and the same per-tile order as cumsum + emit + global 64-bit sort + bin edges
+    (bit-exact), and the same records -- up to the full C2 size the bench runs."""
+    sc = _scene(n, W, H, scale, seed=3 * n, opacity=(0.05, 0.95) if n >= 1_000_000 else (0.05, 0.35))
     if n == 4000:   # duplicate depths: ties must resolve to ascending unsorted slot (stable order)
         sc["means"][:, 2] = np.round(sc["means"][:, 2] * 8) / 8
     _, xys, depths, radii, conics, nth = _project_gpu(sc)
@@ -139,11 +153,9 @@ def test_bucket_binning_matches_generic_sort(n, W, H, scale):
     rng = np.random.default_rng(5)
     colors = cu(rng.uniform(0, 1, (n, 3)).astype(np.float32))
     opac = cu(sc["opacities"])
-    bins_b, cursor, stats = ops.bucket_tile_ranges(xys, radii, tb)
-    m, max_len = (int(v) for v in stats.tolist())
-    assert m == int(cum[-1])
-    rec_b, idx_b, gs_b = ops.bucket_sort_pack(n, m, max_len, xys, depths, radii, cum, tb, bins_b, cursor, conics, colors, opac,
-                                              want_index=True)
+    m, max_len, bins_b, cum_b, stats, rec_b, idx_b, gs_b = _bucket_exact(xys, depths, radii, conics, colors, opac, tb,
+                                                                        cull=False)
+    assert m == int(cum[-1]) and torch.equal(cum_b, cum)
     isect, gids, ks, gs, bins, idx = ops.binAndSortGaussians(n, m, xys, depths, radii, cum, tb, return_index=True)
     assert torch.equal(bins_b, bins)
     assert int((bins[:, 1] - bins[:, 0]).max()) == max_len
@@ -151,8 +163,91 @@ def test_bucket_binning_matches_generic_sort(n, W, H, scale):
     bg = cu(np.zeros(3, np.float32))
     out, fT, fI, rec = ops.rasterize_forward(tb, (W, H, 1), gs, idx, bins, xys, conics, colors, opac, bg)
     assert torch.equal(rec_b[: m * 48], rec[: m * 48])
-    out_b, fT_b, fI_b = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins_b, rec_b, bg)
+    out_b, fT_b, fI_b = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins_b, rec_b, bg, stats)
     assert torch.equal(out, out_b) and torch.equal(fI, fI_b)
+
+
+@pytest.mark.parametrize("n,W,H,scale,opac", [(4000, 256, 256, 0.3, (0.05, 0.35)), (30000, 640, 360, 0.15, (0.01, 0.99)),
+                                              (50, 48, 40, 2.0, (0.3, 0.6)), (200_000, 1024, 576, 0.05, (0.05, 0.95)),
+                                              (1_000_000, 1920, 1080, 0.02, (0.05, 0.95))])
+def test_culled_binning_is_the_generic_lists_minus_untouched_pairs(n, W, H, scale, opac):
+    """cull = 1 (what RasterizeGaussians uses): every tile list is the reference's list minus pairs whose extent box
+    misses the tile, in the same order; image, final_Ts and all four gradients are BIT-identical to the
+    unculled path (the dropped pairs contribute exactly nothing)."""
+    sc = _scene(n, W, H, scale, seed=3 * n + 1, opacity=opac)
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    cum = ops.cumsum_tiles_hit(nth)
+    tb = ops.tile_bounds(W, H)
+    rng = np.random.default_rng(6)
+    colors = cu(rng.uniform(0, 1, (n, 3)).astype(np.float32))
+    op = cu(sc["opacities"])
+    bg = cu(np.array([0.2, 0.1, 0.3], np.float32))
+    m0, _, bins0, cum0, st0, rec0, idx0, gs0 = _bucket_exact(xys, depths, radii, conics, colors, op, tb, cull=False)
+    m1, len1, bins1, cum1, st1, rec1, idx1, gs1 = _bucket_exact(xys, depths, radii, conics, colors, op, tb, cull=True)
+    assert 0 < m1 <= m0
+    if n >= 30000:
+        assert m1 < 0.95 * m0          # the cull does remove pairs on these scenes
+    # per tile: the culled Gaussian list is a subsequence of the reference's list
+    b0, b1, g0, g1 = npy(bins0), npy(bins1), npy(gs0), npy(gs1)
+    lens1 = b1[:, 1] - b1[:, 0]
+    assert lens1.sum() == m1 and lens1.max() == len1
+    for t in np.random.default_rng(0).choice(b0.shape[0], size=min(200, b0.shape[0]), replace=False):
+        full, kept = g0[b0[t, 0]:b0[t, 1]], g1[b1[t, 0]:b1[t, 1]]
+        it = iter(full.tolist())
+        assert all(any(x == y for y in it) for x in kept.tolist()), f"tile {t}: not a subsequence"
+    # cum of the culled path counts the kept pairs per Gaussian
+    per_g = np.bincount(g1[:m1], minlength=n)
+    assert np.array_equal(np.diff(np.concatenate([[0], npy(cum1)])), per_g)
+    out0, fT0, fI0 = ops.rasterize_forward_packed(tb, (W, H, 1), m0, bins0, rec0, bg, st0)
+    out1, fT1, fI1 = ops.rasterize_forward_packed(tb, (W, H, 1), m1, bins1, rec1, bg, st1)
+    assert torch.equal(out0, out1) and torch.equal(fT0, fT1)
+    v_out = cu(rng.uniform(-1, 1, (H, W, 3)).astype(np.float32))
+    ga = ops.rasterize_backward(H, W, n, m0, bins0, conics, op, rec0, cum0, bg, fT0, fI0, v_out)
+    gb = ops.rasterize_backward(H, W, n, m1, bins1, conics, op, rec1, cum1, bg, fT1, fI1, v_out)
+    for a, b in zip(ga, gb):
+        assert torch.equal(a, b)
+
+
+def test_binning_capacity_overflow_is_flagged_and_harmless():
+    """Capacities smaller than the frame needs: stats[2] = 1 and neither the sort/pack nor the blend kernel touch
+    their outputs; the operator redoes the frame with larger capacities and gives the same image."""
+    n, W, H = 20000, 320, 200
+    sc = _scene(n, W, H, 0.2, seed=77)
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    tb = ops.tile_bounds(W, H)
+    colors = cu(np.random.default_rng(1).uniform(0, 1, (n, 3)).astype(np.float32))
+    op = cu(sc["opacities"])
+    bg = cu(np.zeros(3, np.float32))
+    m, max_len, bins, cum, stats, rec, _, _ = _bucket_exact(xys, depths, radii, conics, colors, op, tb, cull=True)
+    ref, _, _ = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins, rec, bg, stats)
+    for m_cap, len_cap in ((m - 1, max_len), (m, max_len - 1), (m // 2, 64)):
+        b2, c2, st2, ws2 = ops.bucket_tile_ranges(xys, radii, conics, colors, op, tb, m_cap, len_cap)
+        assert [int(v) for v in st2.tolist()] == [m, max_len, 1, 0]
+        rec2 = torch.full((capi_records_bytes(m_cap),), 0xAB, dtype=torch.uint8, device=DEV)
+        from opensplat_b200 import capi
+        off = (-ws2.data_ptr()) % 256
+        capi.check(capi.lib().gsb_bucket_sort_pack(n, m_cap, len_cap, capi.ptr(depths), capi.ptr(radii), capi.ptr(c2),
+                                                   1, tb[0], tb[1], capi.ptr(b2), capi.ptr(st2), ws2.data_ptr() + off,
+                                                   ws2.numel() - off, capi.ptr(rec2), None, None, capi.stream()))
+        assert bool((rec2 == 0xAB).all())
+        out = torch.full((H, W, 3), -7.0, device=DEV)
+        fT, fI = torch.empty((H, W), device=DEV), torch.empty((H, W), dtype=torch.int32, device=DEV)
+        capi.check(capi.lib().gsb_rasterize_forward_packed(H, W, tb[0], tb[1], m_cap, capi.ptr(b2), capi.ptr(st2),
+                                                           capi.ptr(bg), capi.ptr(rec2), capi.ptr(out), capi.ptr(fT),
+                                                           capi.ptr(fI), capi.stream()))
+        assert bool((out == -7.0).all())
+    # operator level: plans start too small (fresh plan), the result must not depend on it
+    ops._plans.clear()
+    img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, colors, op, H, W, bg)
+    assert torch.equal(img, ref)
+    ops._plans[torch.device(DEV).index].m_cap = 17     # force one more overflow + redo
+    img2 = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, colors, op, H, W, bg)
+    assert torch.equal(img2, ref)
+
+
+def capi_records_bytes(m):
+    from opensplat_b200 import capi
+    return capi.lib().gsb_raster_records_bytes(m)
 
 
 def test_sort_stability_with_duplicate_keys():
@@ -409,8 +504,8 @@ def test_very_long_tile_lists_take_radix_and_generic_paths(n, expect_path):
     colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
     _, xys, depths, radii, conics, nth = _project_gpu(sc)
     tb = ops.tile_bounds(W, H)
-    bins, cursor, stats = ops.bucket_tile_ranges(xys, radii, tb)
-    m, max_len = (int(v) for v in stats.tolist())
+    _, _, stats, _ = ops.bucket_tile_ranges(xys, radii, conics, cu(colors), cu(sc["opacities"]), tb, 0, 0)
+    m, max_len = (int(v) for v in stats.tolist()[:2])
     cap = capi.lib().gsb_bucket_max_tile_len()
     assert (max_len > 4096 and max_len <= cap) if expect_path == "radix" else (max_len > cap)
     colt, opt = cu(colors).requires_grad_(), cu(sc["opacities"]).requires_grad_()

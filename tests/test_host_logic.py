@@ -9,7 +9,7 @@ from opensplat_b200.scene import make_scene, rotated_camera
 def test_workspace_queries_are_monotone_and_aligned():
     L = capi.lib()
     for fn in (L.gsb_sort_workspace_bytes, L.gsb_raster_records_bytes, L.gsb_raster_grad_rows_bytes,
-               (lambda m: L.gsb_bucket_workspace_bytes(1000, m)), L.gsb_cumsum_workspace_bytes):
+               (lambda m: L.gsb_bucket_workspace_bytes(1000, m, 8160)), L.gsb_cumsum_workspace_bytes):
         prev = 0
         for m in (0, 1, 100, 2048, 2049, 1_000_000, 50_000_000):
             b = fn(m)
@@ -17,7 +17,8 @@ def test_workspace_queries_are_monotone_and_aligned():
             prev = b
     assert L.gsb_raster_records_bytes(1000) >= 1000 * 48 + 256        # 48-B records + the scratch words
     assert L.gsb_raster_grad_rows_bytes(1000) >= 1000 * 48
-    assert L.gsb_bucket_cursor_bytes(8160) == 8160 * 128              # one 128-B line per tile
+    # bucket workspace: header + scan states + one 128-B counter line per tile + 48-B attribute records + 12 B / slot
+    assert L.gsb_bucket_workspace_bytes(1000, 5000, 8160) >= 256 + 8160 * 128 + 1000 * 48 + 5000 * 12
     assert L.gsb_bucket_max_tile_len() == 16384
     assert L.gsb_ssim_workspace_bytes(1080, 1920) >= 3 * 1080 * 1920 * 3 * 4
 
@@ -45,6 +46,12 @@ def test_flat_layout_matches_pipeline_order():
     names = sorted(offs, key=lambda k: offs[k][0])
     assert names == ["means", "scales", "quats", "opacities", "coeffs"]   # geometry prefix, SH coefficients last
     assert offs["coeffs"][0] == 1000 * 11
+    # odd Gaussian counts (any refinement can leave one): every slice still starts on a 16-byte boundary
+    for n in (1, 3, 257, 1001, 99_999):
+        offs, total = parallel.flat_layout(n, 16)
+        assert all(o % 4 == 0 for o, _, _ in offs.values()) and total % 4 == 0
+        ends = sorted((o, o + c) for o, c, _ in offs.values())
+        assert all(a[1] <= b[0] for a, b in zip(ends[:-1], ends[1:])) and ends[-1][1] <= total
 
 
 def test_refine_schedule_matches_reference_defaults():
