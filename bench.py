@@ -6,8 +6,8 @@
 
 Workload (BASELINE.json configs[1]): 1M synthetic Gaussians, 1920x1080, SH degree 3, fp32, one camera
 view per GPU (data-parallel over views; weak scaling).  A "step" is one pass of the hot path over one
-view: SH fwd -> project fwd -> scan/emit/sort/bins -> blend fwd -> MSE -> blend bwd -> project bwd ->
-SH bwd (+ one NCCL all-reduce of the flat per-Gaussian gradient buffer when N > 1).  Prints ONE JSON line.
+view: SH fwd -> project fwd -> bin/sort/pack -> blend fwd -> MSE -> blend bwd -> project bwd -> SH bwd
+(+ the cross-GPU gradient exchange when N > 1).  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -27,12 +27,14 @@ WORKLOADS = {
     "c5_5M_1440p_dense": (5_000_000, 2560, 1440, 0.023, (0.05, 0.95)),   # ~200 blended-candidate splats / pixel
     "c1_1k_256": (1_000, 256, 256, 0.5, (0.05, 0.95)),
 }
-# kernels of OURS launched per fwd+bwd step (counted from the C-ABI implementations, bucket fast path):
-#   project_fwd 1, cumsum 3, tile_count 1, tile_scan 1, sh_fwd(+clamp) 1, bucket_emit 1, tile_sort_pack 1,
-#   blend_fwd 1, mse 1, blend_bwd 1, row_reduce 1, project_bwd 1, sh_bwd 1 (N>1 fused exchange: mask 1 + multiview 1)
+
+
+# kernels of OURS launched per fwd+bwd step (counted from the C-ABI implementations, fast binning path):
+#   sh_fwd(+clamp) 1, project_fwd 1, bin_count_scan 1, tile_scan 1, bucket_emit 1, tile_sort_pack 1, blend_fwd 1,
+#   mse 1, blend_bwd 1, row_reduce 1, project_bwd 1, sh_bwd 1
+#   (N>1 fused exchange: mask 1 + exchange 1 instead of sh_bwd; the two cross-rank barriers are torch's kernels)
 def launches_per_step(world=1, fused=True, train=False):
-    n = 1 + 3 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1
-    n += 2 if (world > 1 and fused) else 1
+    n = 11 + (2 if (world > 1 and fused) else 1)
     return n + (1 if train else 0)
 
 
@@ -94,24 +96,22 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(workload, steps=1, warmup=1):
-    """Times the reference's own CPU back end (oracle/_ref: unmodified gsplat_cpu.cpp + operator .cpp
-    files) on a bounded sample of the workload: a 1/16-area window (W/4 x H/4) holding N/16 Gaussians with
-    the same per-pixel splat density and the same pixel footprint distribution (scale x4 because the focal
-    length scales with W).  Returns (Mpixel/s, dict)."""
+def cpu_reference_run(workload, steps, warmup, budget_s):
+    """Times the reference's own CPU back end (oracle/_ref: the unmodified gsplat_cpu.cpp + operator .cpp files
+    compiled where they lie) on the FULL workload -- same Gaussians, same image size, same fwd+bwd step as the
+    GPU arm.  `steps` timed repetitions after `warmup` untimed ones, cut short once `budget_s` seconds of timed
+    work have been spent (at least one timed step always runs).  Returns (Mpixel/s, info)."""
     import numpy as np
     import torch
     from oracle import ref
     from opensplat_b200.scene import make_scene
     n, W, H, scale, opac = WORKLOADS[workload]
-    div = 2 if n >= 16_000 else 1
-    ns, Ws, Hs = n // (div * div), W // div, H // div
-    sc = make_scene(ns, Ws, Hs, scale=scale * div, sh_degree=3, opacity=opac, seed=0)
+    sc = make_scene(n, W, H, scale=scale, sh_degree=3, opacity=opac, seed=0)
     o = ref.ops()
     # all the host threads the reference can use (torchrun exports OMP_NUM_THREADS=1 to its workers)
     torch.set_num_threads(max(torch.get_num_threads(), min(os.cpu_count() or 1, 64)))
     t = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).requires_grad_(g)
-    target = torch.zeros(Hs, Ws, 3)
+    target = torch.zeros(H, W, 3)
     times = []
     for it in range(warmup + steps):
         means, scales, quats = t(sc["means"], True), t(sc["scales"], True), t(sc["quats"], True)
@@ -119,35 +119,38 @@ def cpu_reference_sample(workload, steps=1, warmup=1):
         t0 = time.perf_counter()
         rgbs = torch.clamp_min(o.sh_cpu(3, t(sc["viewdirs"]), coeffs) + 0.5, 0.0)
         p = o.project_cpu(means, scales, 1.0, quats, t(sc["viewmat"]), t(sc["projmat"]), sc["fx"], sc["fy"],
-                          sc["cx"], sc["cy"], Hs, Ws, 0.01)
-        img = o.rasterize_cpu(p[0], p[1], p[2], rgbs, opacity, p[3], p[4].contiguous(), Hs, Ws, torch.zeros(3))
+                          sc["cx"], sc["cy"], H, W, 0.01)
+        img = o.rasterize_cpu(p[0], p[1], p[2], rgbs, opacity, p[3], p[4].contiguous(), H, W, torch.zeros(3))
         loss = torch.nn.functional.mse_loss(img, target)
         loss.backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+            if sum(times) >= budget_s:
+                break
     sec = sum(times) / len(times)
-    info = {"cores": int(o.num_threads()), "kind": "reference",
-            "sample": f"{ns} Gaussians at {Ws}x{Hs} (1/{div*div}-area window of {workload}, same splats/pixel and "
-                      f"pixel footprints), fwd+bwd, {steps} timed step(s); raster loops of the reference are "
-                      f"single-threaded, ATen ops use {int(o.num_threads())} threads; host has {os.cpu_count()} cpus",
+    info = {"cores": int(o.num_threads()), "kind": "reference", "steps_timed": len(times), "warmup_done": warmup,
+            "sample": f"the full workload ({n} Gaussians at {W}x{H}, SH degree 3, fwd+bwd), {len(times)} timed "
+                      f"step(s) after {warmup} warm-up; raster loops of the reference are single-threaded, ATen ops "
+                      f"use {int(o.num_threads())} threads; host has {os.cpu_count()} cpus",
             "seconds_per_step": sec}
-    return Ws * Hs / sec / 1e6, info
+    return W * H / sec / 1e6, info
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    v, info = cpu_reference_sample(args.workload, steps=steps, warmup=warmup)
+    warmup = max(0, min(args.warmup, 1))   # a CPU loop has nothing to warm beyond the allocator: one step at most
+    v, info = cpu_reference_run(args.workload, steps=max(1, args.steps), warmup=warmup, budget_s=args.ref_budget_s)
     n, W, H, scale, opac = WORKLOADS[args.workload]
     out = {"impl": "reference", "metric": "fwd_bwd_mpixel_per_s", "value": v, "unit": "Mpixel/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "n_gpus": args.gpus, "steps": info["steps_timed"], "warmup": info["warmup_done"],
            "ms_per_step": info["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "gaussians": n, "width": W, "height": H, "sh_degree": 3,
-                      "note": f"bounded sample, {steps} timed step(s) (requested {args.steps})"},
+                      "note": f"full workload; {info['steps_timed']} step(s) timed of {args.steps} requested "
+                              f"(time budget {args.ref_budget_s:.0f} s of CPU work), {info['warmup_done']} warm-up"},
            "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": info["cores"], "kind": "reference",
                             "sample": info["sample"]},
            "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -155,13 +158,118 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _setup_pipe(workload, dev, rank, world, stage_timing=True):
+    import numpy as np
+    import torch
+    from opensplat_b200.pipeline import SplatPipeline
+    from opensplat_b200.scene import make_scene, cube_view_camera
+    n, W, H, scale, opac = WORKLOADS[workload]
+    sc = make_scene(n, W, H, scale=scale, sh_degree=3, opacity=opac, seed=0)  # same Gaussians on every rank
+    pipe = SplatPipeline(n, W, H, sh_degree=3, device=dev, stage_timing=stage_timing)
+    pipe.load_scene(sc)
+    cam = None
+    if world > 1:  # one camera view per GPU (config C4): the eight cube-symmetry views (comparable work per rank)
+        cam = cube_view_camera(W, H, rank)
+        pipe.set_camera(cam)
+        vd = sc["means"] - cam["cam_pos"]
+        vd = (vd / np.linalg.norm(vd, axis=-1, keepdims=True)).astype(np.float32)
+        pipe.viewdirs.copy_(torch.from_numpy(vd).to(dev))
+    rng = np.random.default_rng(1 + rank)
+    target_host = torch.from_numpy(rng.uniform(0, 1, (H, W, 3)).astype(np.float32)).pin_memory()
+    pipe.target.copy_(target_host, non_blocking=True)
+    return pipe, sc, cam, target_host
+
+
+def _pair_counts(pipe):
+    """Untimed diagnostic pass: work units of the blend kernels for the frame currently in the pipeline's buffers."""
+    import torch
+    from opensplat_b200 import capi
+    L, P = capi.lib(), capi.ptr
+    cnt = torch.zeros(4, dtype=torch.int64, device=pipe.dev)
+    out = torch.empty_like(pipe.out_img)
+    fT, fI = torch.empty_like(pipe.final_Ts), torch.empty_like(pipe.final_idx)
+    capi.check(L.gsb_rasterize_forward_count(pipe.H, pipe.W, pipe.tb[0], pipe.tb[1], pipe.m_raster, P(pipe.tile_bins),
+                                             P(pipe.background), P(pipe.records), P(out), P(fT), P(fI), P(cnt),
+                                             capi.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, pipe.out_img), "counting instantiation must reproduce the production image"
+    rec, slots, ev, bl = (int(v) for v in cnt.tolist())
+    return {"records_processed": rec, "pixel_tests": slots * 32, "pairs_evaluated": ev, "pairs_blended": bl}
+
+
+def _traffic_for(workload, kernel):
+    """dram__bytes_read+write of one launch from this round's `ncu --set full` capture, if one exists for exactly
+    this workload and kernel (profiles/dram_traffic.json); null otherwise -- never a number from another config."""
+    tfile = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        d = json.load(open(tfile))
+        return d.get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+def _roofline(pipe, stage_ms, ms_step, workload, pairs):
+    peak, peak_src = peaks()
+    alg, passes = pipe.algorithmic_bytes()
+    alg_stage = dict(alg)
+    alg_stage["bucket_sort_pack"] = alg["emit"] + alg["sort"] + alg["bins"]   # the fused stage stands for the three rows
+    dom = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else "raster_bwd"
+    dom_key = dom if dom in alg_stage else "raster_bwd"
+    ach = alg_stage[dom_key] / (stage_ms.get(dom_key, ms_step) * 1e-3) / 1e9
+    path_bytes = sum(v for k, v in alg.items())
+    path_ach = path_bytes / (ms_step * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom_key, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": _traffic_for(workload, dom_key), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_stage[dom_key], "ms_per_launch": stage_ms.get(dom_key),
+            "note": "both blend kernels are instruction-issue bound (SURVEY R6); their work units are pixel pairs, "
+                    "see `pairs`"}
+    if pairs:
+        f, b = stage_ms.get("raster_fwd"), stage_ms.get("raster_bwd")
+        roof["pairs"] = dict(pairs)
+        if f:
+            roof["pairs"]["fwd_blended_pairs_per_s"] = pairs["pairs_blended"] / (f * 1e-3)
+            roof["pairs"]["fwd_evaluated_pairs_per_s"] = pairs["pairs_evaluated"] / (f * 1e-3)
+        if b:   # the backward pass replays the same blended set (up to each pixel's final index)
+            roof["pairs"]["bwd_blended_pairs_per_s"] = pairs["pairs_blended"] / (b * 1e-3)
+            roof["pairs"]["bwd_evaluated_pairs_per_s"] = pairs["pairs_evaluated"] / (b * 1e-3)
+    roof_path = {"achieved": path_ach, "peak": peak, "unit": "GB/s", "frac": path_ach / peak,
+                 "algorithmic_bytes_per_step": path_bytes, "generic_sort_passes_modelled": passes}
+    return roof, roof_path
+
+
+def _side_config(workload, dev, steps=5, warmup=3):
+    """One-shot sub-record for another BASELINE config (C3 / C5) on this GPU: value, stages, roofline."""
+    import torch
+    pipe, sc, cam, tgt = _setup_pipe(workload, dev, 0, 1, stage_timing=True)
+    for _ in range(warmup):
+        pipe.forward_backward()
+    pipe.stage_ms.clear(); pipe._steps_ev = []
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pipe.forward_backward()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    stage_ms = pipe.resolve_stage_times()
+    pairs = _pair_counts(pipe)
+    roof, roof_path = _roofline(pipe, stage_ms, ms, workload, pairs)
+    n, W, H, _, _ = WORKLOADS[workload]
+    rec = {"value": W * H / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "gaussians": n, "width": W, "height": H, "intersections_binned": pipe.m,
+           "intersections_reference": int(pipe.nth.sum()), "longest_tile_list": pipe.max_len,
+           "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "roofline": roof, "roofline_path": roof_path}
+    del pipe
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from opensplat_b200 import capi, ops
-    from opensplat_b200.pipeline import SplatPipeline
-    from opensplat_b200.scene import make_scene, rotated_camera
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,26 +281,15 @@ def run_ours(args):
     capi.lib()  # fail loudly if the CUDA library is missing
 
     n, W, H, scale, opac = WORKLOADS[args.workload]
-    sc = make_scene(n, W, H, scale=scale, sh_degree=3, opacity=opac, seed=0)  # same Gaussians on every rank
-    pipe = SplatPipeline(n, W, H, sh_degree=3, device=dev, stage_timing=True)
-    pipe.load_scene(sc)
-    if world > 1:  # one camera view per GPU (config C4): orbit the scene
-        cam = rotated_camera(W, H, rank, n_views=max(world, 8))
-        pipe.set_camera(cam)
-        vd = sc["means"] - cam["cam_pos"]
-        vd = (vd / np.linalg.norm(vd, axis=-1, keepdims=True)).astype(np.float32)
-        pipe.viewdirs.copy_(torch.from_numpy(vd).to(dev))
-    rng = np.random.default_rng(1 + rank)
-    target_host = torch.from_numpy(rng.uniform(0, 1, (H, W, 3)).astype(np.float32)).pin_memory()
-    pipe.target.copy_(target_host, non_blocking=True)
-
-    if world > 1 and args.exchange == "fused":
+    pipe, sc, cam, target_host = _setup_pipe(args.workload, dev, rank, world)
+    fused = world > 1 and args.exchange == "fused"
+    if fused:
         from opensplat_b200.multigpu import ViewParallelExchange
         pipe.exchange = ViewParallelExchange(pipe, cam["cam_pos"])
 
     def step_fwd_bwd():
         pipe.forward()
-        pipe.backward()       # with pipe.exchange: fused multi-view SH backward + NVLink exchange inside
+        pipe.backward()       # with pipe.exchange: fused multi-view SH backward + gradient all-reduce inside
         if world > 1 and pipe.exchange is None:
             dist.all_reduce(pipe.grad_flat, op=dist.ReduceOp.SUM)
         pipe._collect()
@@ -224,9 +321,21 @@ def run_ours(args):
     ms_total = timed(step_fwd_bwd, args.steps)
     stage_ms = pipe.resolve_stage_times()
     m_timed = pipe.m
-    alg, passes = pipe.algorithmic_bytes()
     ms_step = ms_total / args.steps
     value = world * W * H / (ms_step * 1e-3) / 1e6
+    pairs = _pair_counts(pipe)
+    m_ref = int(pipe.nth.sum())
+
+    # per-rank work and compute time (separates view skew from the exchange): every rank's binned M, longest tile
+    # list and the sum of its own stages without the exchange stage
+    compute_ms = sum(v for k, v in stage_ms.items() if k != "sh_bwd")
+    mine = {"rank": rank, "intersections_binned": m_timed, "intersections_reference": m_ref,
+            "longest_tile_list": pipe.max_len, "compute_ms_without_exchange": round(compute_ms, 4),
+            "exchange_stage_ms": round(stage_ms.get("sh_bwd", 0.0), 4)}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
     # ---- train iters/s: + fused Adam (and the all-reduce average) ----
     pipe.stage_timing = False
@@ -234,24 +343,31 @@ def run_ours(args):
         pipe.train_step(world_size=world)
     ms_train = timed(lambda: pipe.train_step(world_size=world), args.steps) / args.steps
 
-    # ---- e2e: through the autograd operators (ops.py), host buffers in the timed region ----
-    P = {k: pipe.p[k].detach().clone().requires_grad_() for k in ("means", "scales", "quats", "coeffs", "opacities")}
+    # ---- e2e: through the reference-facing autograd operators, host buffers in the timed region ----
+    from opensplat_b200 import cpp_ops
+    use_cpp = cpp_ops.available()
+    cops = cpp_ops.ops() if use_cpp else None
+    names = ("means", "scales", "quats", "coeffs", "opacities")
+    P = {k: pipe.p[k].detach().clone().requires_grad_() for k in names}
+    # the operators' gradients accumulate IN PLACE into views of one flat buffer (AccumulateGrad adds into an existing
+    # .grad), so the data-parallel exchange of this arm is the single NCCL all-reduce of north_star
+    gflat = torch.zeros(sum(t.numel() for t in P.values()), device=dev)
+    gviews, o = {}, 0
+    for k in names:
+        gviews[k] = gflat[o:o + P[k].numel()].view_as(P[k]); o += P[k].numel()
     view_host = pipe.viewmat.cpu().pin_memory()
     proj_host = pipe.projmat.cpu().pin_memory()
     fx, fy, cx, cy = pipe.intr
     bg = torch.zeros(3, device=dev)
-    loss_host = torch.zeros(1).pin_memory()
-
-    from opensplat_b200 import cpp_ops
-    use_cpp = cpp_ops.available()
-    cops = cpp_ops.ops() if use_cpp else None
 
     # H2D of every step's inputs (target image + camera) from pinned memory runs on a copy stream, one step
-    # ahead of the compute (double buffer), so PCIe overlaps the kernels; it is still inside the timed region.
+    # ahead of the compute (double buffer); the step's result (the loss) is copied D2H every step into one of two
+    # pinned slots and consumed one step later, so neither direction stalls the GPU.  All inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
     slots = [dict(tgt=torch.empty_like(pipe.target), vm=torch.empty_like(pipe.viewmat),
-                  pm=torch.empty_like(pipe.projmat), ev=torch.cuda.Event(), used=torch.cuda.Event()) for _ in range(2)]
-    state = {"i": 0}
+                  pm=torch.empty_like(pipe.projmat), ev=torch.cuda.Event(), used=torch.cuda.Event(),
+                  loss=torch.zeros(1).pin_memory(), loss_ev=torch.cuda.Event()) for _ in range(2)]
+    state = {"i": 0, "last_loss": None}
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
@@ -266,13 +382,22 @@ def run_ours(args):
     prefetch(slots[0])
 
     def step_e2e():
-        cur = slots[state["i"] % 2]
-        prefetch(slots[(state["i"] + 1) % 2])                    # next step's inputs, overlapped
-        state["i"] += 1
+        i = state["i"]
+        cur, nxt = slots[i % 2], slots[(i + 1) % 2]
+        if i > 0:                                                # the PREVIOUS step's result, read on the host
+            nxt["loss_ev"].synchronize()
+            state["last_loss"] = float(nxt["loss"][0])
+        prefetch(nxt)                                            # next step's inputs, overlapped
+        state["i"] = i + 1
         torch.cuda.current_stream().wait_event(cur["ev"])       # this step's H2D has landed
         tgt, vm, pm = cur["tgt"], cur["vm"], cur["pm"]
-        for t in P.values():
-            t.grad = None
+        if world > 1:
+            gflat.zero_()
+            for k in names:
+                P[k].grad = gviews[k]
+        else:
+            for t in P.values():
+                t.grad = None
         if use_cpp:   # the libtorch autograd operators a C++ caller of the reference API uses
             rgbs = torch.clamp_min(cops.spherical_harmonics(3, pipe.viewdirs, P["coeffs"]) + 0.5, 0.0)
             xys, depths, radii, conics, nth, _ = cops.project_gaussians(
@@ -286,11 +411,10 @@ def run_ours(args):
         loss = torch.nn.functional.mse_loss(img, tgt)
         loss.backward()
         if world > 1:
-            for t in P.values():
-                dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
+            dist.all_reduce(gflat, op=dist.ReduceOp.SUM)        # ONE flat all-reduce of all per-Gaussian gradients
         cur["used"].record(torch.cuda.current_stream())
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # D2H: the step's result
-        torch.cuda.current_stream().synchronize()
+        cur["loss"].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H: the step's result
+        cur["loss_ev"].record(torch.cuda.current_stream())
 
     for _ in range(3):
         step_e2e()
@@ -298,63 +422,61 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * W * H / (ms_e2e * 1e-3) / 1e6
 
-    # ---- roofline of the dominant stage ----
-    peak, peak_src = peaks()
-    # the fused two-level binning stage stands for SURVEY's emit + sort + bins rows
-    alg_stage = dict(alg)
-    alg_stage["bucket_sort_pack"] = alg["emit"] + alg["sort"] + alg["bins"]
-    dom = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else "raster_bwd"
-    dom_key = dom if dom in alg_stage else "raster_bwd"
-    alg = alg_stage if dom_key == "bucket_sort_pack" else alg
-    ach = alg[dom_key] / (stage_ms.get(dom_key, ms_step) * 1e-3) / 1e9
-    path_bytes = sum(v for k, v in alg.items() if k != "bucket_sort_pack")
-    path_ach = path_bytes / (ms_step * 1e-3) / 1e9
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tfile):
-        try:
-            traffic = json.load(open(tfile)).get(dom_key)
-        except Exception:
-            traffic = None
+    roof, roof_path = _roofline(pipe, stage_ms, ms_step, args.workload, pairs)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    side = {}
+    if world == 1 and args.workload == "c2_1M_1080p_sh3" and not args.no_side_configs:
+        del P, gflat
+        for wl in ("c3_3M_4k_sh3", "c5_5M_1440p_dense"):
+            try:
+                side[wl] = _side_config(wl, dev)
+            except Exception as ex:   # a sub-record must never cost the headline line
+                side[wl] = {"error": str(ex)[:300]}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, info = cpu_reference_sample(args.workload, steps=2, warmup=1)
+            v, info = cpu_reference_run(args.workload, steps=2, warmup=0, budget_s=30.0)
             cpu = {"value": v, "unit": "Mpixel/s", "cores": info["cores"], "kind": info["kind"],
                    "sample": info["sample"]}
         except Exception as ex:  # the checker is optional for the number; say why it is missing
             cpu = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
 
+    exch = ("fused launch: multi-view SH bwd over NVLink peer loads + two-shot all-reduce of the geometry gradients ("
+            + ("NVSwitch multimem" if getattr(pipe.exchange, "multicast_ptr", 0) else "peer pointers") + ")") \
+        if fused else "nccl all-reduce(flat grads)"
     out = {
         "metric": "fwd_bwd_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "gaussians": n, "width": W, "height": H, "sh_degree": 3,
-                   "intersections_M": m_timed, "views_per_gpu": 1, "parallelism": f"dp{world}-views",
-                   "step": "sh+project+scan/emit/sort/bins+blend fwd, mse, blend+project+sh bwd"
-                           + ((", fused multi-view SH bwd over NVLink peer loads + nccl allreduce(geometry grads)"
-                               if args.exchange == "fused" else ", nccl allreduce(flat grads)") if world > 1 else ""),
+                   "intersections_M": m_timed, "intersections_reference": m_ref,
+                   "binning": "conservative cull at bin time: (Gaussian, tile) pairs whose alpha>=1/255 extent box "
+                              "misses the tile are never sorted or streamed (results unchanged)",
+                   "views_per_gpu": 1, "parallelism": f"dp{world}-views",
+                   "views": "cube-symmetry view set (comparable work per rank)" if world > 1 else "front view",
+                   "step": "sh+project+bin/sort/pack+blend fwd, mse, blend+project+sh bwd"
+                           + (", " + exch if world > 1 else ""),
                    "l2_policy": "inputs larger than L2 (>300 MB of parameters/records per step vs 126 MB L2)"},
         "train_iters_per_s": 1e3 / ms_train, "train_ms_per_iter": ms_train,
         "e2e": {"value": e2e_value, "unit": "Mpixel/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(target_host.numel() * 4 + 128), "d2h_bytes_per_step": 4 + 4,
+                "h2d_bytes_per_step": int(target_host.numel() * 4 + 128), "d2h_bytes_per_step": 4 + 16,
+                "last_loss_read_on_host": state["last_loss"],
                 "api": ("C++ libtorch autograd operators ProjectGaussians/RasterizeGaussians/SphericalHarmonics "
                         "(libopensplat_b200_ops.so via torch.ops)") if use_cpp else
-                       "opensplat_b200.ops python autograd operators"},
-        "gpu_launches": launches_per_step(world, args.exchange == "fused") * args.steps,
+                       "opensplat_b200.ops python autograd operators",
+                "exchange": "one NCCL all-reduce of the flat gradient buffer" if world > 1 else None},
+        "gpu_launches": launches_per_step(world, fused) * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": dom_key, "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg[dom_key], "ms_per_launch": stage_ms.get(dom_key)},
-        "roofline_path": {"achieved": path_ach, "peak": peak, "unit": "GB/s", "frac": path_ach / peak,
-                          "algorithmic_bytes_per_step": path_bytes, "sort_passes": passes},
+        "roofline": roof, "roofline_path": roof_path,
         "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+        "per_rank": per_rank,
+        "other_configs": side or None,
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))
@@ -382,8 +504,12 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_1M_1080p_sh3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the C3 / C5 one-shot sub-records (N=1)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="--impl reference: stop after this many seconds of timed CPU work (>= 1 step always runs)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N>1: fused multi-view SH backward over peer memory (default) or plain NCCL all-reduce")
+                    help="N>1: fused multi-view SH backward + all-reduce launch over peer memory (default) or plain "
+                         "NCCL all-reduce of the flat gradient buffer")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

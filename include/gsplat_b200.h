@@ -76,6 +76,18 @@ int gsb_mask_rgb_grad(int n, const float *rgbs, float *v_rgbs, gsb_stream_t stre
 int gsb_sh_backward_multiview(int n, int degree, int degrees_to_use, const float *means, int num_views,
                               const float *cam_positions, const float *const *v_rgbs_per_view, float scale,
                               float *v_coeffs, gsb_stream_t stream);
+/* gsb_exchange_gradients: the whole data-parallel exchange step as ONE launch -- gsb_sh_backward_multiview plus
+ *   a two-shot all-reduce (x scale) of the remaining per-Gaussian gradients, the first geom_floats floats
+ *   (multiple of 4, 16-byte aligned) of every rank's flat gradient buffer: rank r owns slice r; with NVSwitch
+ *   multicast (geom_multicast = the multicast mapping of that buffer) it is one multimem.ld_reduce + one
+ *   multimem.st per 16 bytes, otherwise (geom_multicast NULL) the slice is summed from and written to the
+ *   peer-mapped pointers geom_per_rank[0..world) (device array; world <= 16).  The caller provides the two
+ *   cross-rank barriers around the launch (all inputs written / all results visible).  Replaces the single
+ *   ncclAllReduce of the flat gradient buffer the data-parallel path would otherwise need. */
+int gsb_exchange_gradients(int n, int degree, int degrees_to_use, const float *means, int num_views,
+                           const float *cam_positions, const float *const *v_rgbs_per_view, float scale,
+                           float *v_coeffs, int rank, int world, long long geom_floats,
+                           float *const *geom_per_rank, float *geom_multicast, gsb_stream_t stream);
 
 /* ---- Projection ------------------------------------------------------------------------------
  * gsb_project_forward replaces project_gaussians_forward_tensor (bindings.h:42-65,
@@ -192,6 +204,13 @@ int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tiles_y, int m,
                           const float *colors, const float *opacities, const float *background,
                           void *records, float *out_img, float *final_Ts, int32_t *final_idx,
                           gsb_stream_t stream);
+/* gsb_rasterize_forward_count: diagnostic twin of gsb_rasterize_forward_packed (same outputs) that also ACCUMULATES
+ *   into pair_counts (device uint64[4]; zero it first) {records that pass the per-record extent test, slot visits
+ *   (x 32 lanes = pixel tests), pixel pairs evaluated (sigma inside the extent: one ex2), pixel pairs blended} --
+ *   the work units SURVEY.md 8(d) asks the blend kernels' throughput to be quoted in.  Never on a timed path. */
+int gsb_rasterize_forward_count(int img_h, int img_w, int tiles_x, int tiles_y, int m, const int32_t *tile_bins,
+                                const float *background, void *records, float *out_img, float *final_Ts,
+                                int32_t *final_idx, unsigned long long *pair_counts, gsb_stream_t stream);
 int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
                            const int32_t *tile_bins, const float *conics, const float *opacities,
                            void *records, const int32_t *cum_tiles_hit, const float *background,

@@ -51,12 +51,18 @@ pack_records_kernel(int m, const int *__restrict__ gaussian_ids_sorted,
 #ifndef GSB_FWD_MINB
 #define GSB_FWD_MINB 8   // 64 registers -> 8 CTAs (32 warps) per SM; measured +6 % over the unconstrained build
 #endif
+// COUNT = true is a diagnostic instantiation (gsb_rasterize_forward_count): same arithmetic, plus per-launch
+// totals of {records that pass the per-record test, slot visits, pixel pairs whose sigma is inside the
+// extent (ex2 evaluated), pixel pairs blended} in pair_counts[0..3].  The production instantiation carries none
+// of it.
+template <bool COUNT>
 __global__ void __launch_bounds__(RK_THREADS, GSB_FWD_MINB)
 rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                          const int2 *__restrict__ tile_bins, const GsbRecord *__restrict__ records,
                          const float *__restrict__ background, float *__restrict__ out_img,
                          float *__restrict__ final_Ts, int *__restrict__ final_idx,
-                         unsigned *__restrict__ tile_counter, const int *__restrict__ bin_stats) {
+                         unsigned *__restrict__ tile_counter, const int *__restrict__ bin_stats,
+                         unsigned long long *__restrict__ pair_counts) {
     // bin_stats (optional): stats of gsb_bucket_tile_ranges; [2] != 0 means the binning overflowed its
     // capacities and wrote nothing -- the host redoes the frame, this launch must not touch the records
     if (bin_stats && bin_stats[2]) return;
@@ -71,6 +77,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
     __syncwarp();
     const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
     unsigned gchunk = 0;  // chunks this warp has pushed through its ring so far (stage / parity bookkeeping)
+    unsigned long long n_rec = 0, n_slot = 0, n_eval = 0, n_blend = 0;   // COUNT only
 
     while (true) {
         int tile = 0;
@@ -126,6 +133,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
             unsigned my_mask = 0;
             if (lane < cnt) my_mask = record_slot_mask(ring.rec[s][lane], tile_x0, tile_y0);
             unsigned live = __ballot_sync(0xffffffffu, my_mask != 0u);
+            if (COUNT && lane == 0) n_rec += __popc(live);
             while (live) {
                 const int t = __ffs(live) - 1;
                 live &= live - 1;
@@ -147,9 +155,11 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         const float dy = dy0 - (float)(2 * j);  /* centre.y - pixel row */                                                                    \
         /* sigma = (a/2)dx^2 + (c/2)dy^2 + b dx dy   (forward.cu:340-342) */                              \
         const float sigma = fmaf(dy, fmaf(q1.z, dy, bdx), adx2);                                          \
+        if (COUNT && lane == 0) ++n_slot;                                                                 \
         if (__float_as_uint(sigma) <= __float_as_uint(smax)) { /* 0 <= sigma <= smax, no exp */           \
             /* alpha = min(0.999, opac*exp(-sigma)) = min(0.999, 2^(log2 opac - sigma log2 e)) */         \
             const float alpha = fminf(0.999f, ex2_approx(fmaf(sigma, -GSB_LOG2E, q0.z)));                 \
+            if (COUNT) ++n_eval;                                                                          \
             if (alpha >= (1.f / 255.f)) {                                                                 \
                 const float next_T = T[j] * (1.f - alpha);                                                \
                 if (next_T <= 1e-4f) { /* terminate BEFORE blending */                                    \
@@ -161,6 +171,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                     cb[j] = fmaf(q2.z, vis, cb[j]);                                                       \
                     T[j] = next_T;                                                                        \
                     last[j] = idx0 + t;                                                                   \
+                    if (COUNT) ++n_blend;                                                                 \
                 }                                                                                         \
             }                                                                                             \
         }                                                                                                 \
@@ -215,6 +226,17 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
             }
         }
     }
+    if (COUNT) {
+        // per-lane pixel-pair counts of one persistent warp stay far below 2^27, so the 32-bit warp sums are exact
+        n_eval = __reduce_add_sync(0xffffffffu, (unsigned)n_eval);
+        n_blend = __reduce_add_sync(0xffffffffu, (unsigned)n_blend);
+        if (lane == 0) {
+            atomicAdd(pair_counts + 0, n_rec);
+            atomicAdd(pair_counts + 1, n_slot);
+            atomicAdd(pair_counts + 2, n_eval);
+            atomicAdd(pair_counts + 3, n_blend);
+        }
+    }
 }
 
 }  // namespace
@@ -249,10 +271,11 @@ extern "C" int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tile
         reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
     GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
     const int num_tiles = tiles_x * tiles_y;
-    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel, num_tiles);
-    rasterize_forward_kernel<<<grid, RK_THREADS, 0, s>>>(
+    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel<false>, num_tiles);
+    rasterize_forward_kernel<false><<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr);
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr,
+        nullptr);
     GSB_LAUNCH_CHECK();
     return 0;
 }
@@ -270,10 +293,36 @@ extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, i
         reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
     GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
     const int num_tiles = tiles_x * tiles_y;
-    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel, num_tiles);
-    rasterize_forward_kernel<<<grid, RK_THREADS, 0, s>>>(
+    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel<false>, num_tiles);
+    rasterize_forward_kernel<false><<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, bin_stats);
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, bin_stats,
+        nullptr);
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Diagnostic twin of gsb_rasterize_forward_packed: same outputs, plus pair_counts (device uint64[4], accumulated --
+// zero it first) = {records passing the per-record test, slot visits (x 32 = pixel tests), pixel pairs evaluated
+// (sigma inside the extent), pixel pairs blended}.  Used by bench.py / the profiles for pairs-per-second figures;
+// never on the timed path.
+extern "C" int gsb_rasterize_forward_count(int img_h, int img_w, int tiles_x, int tiles_y, int m,
+                                           const int32_t *tile_bins, const float *background, void *records,
+                                           float *out_img, float *final_Ts, int32_t *final_idx,
+                                           unsigned long long *pair_counts, gsb_stream_t stream) {
+    GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0 && pair_counts);
+    GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
+    GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx && records);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned *counters = reinterpret_cast<unsigned *>(
+        reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
+    GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
+    const int num_tiles = tiles_x * tiles_y;
+    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel<true>, num_tiles);
+    rasterize_forward_kernel<true><<<grid, RK_THREADS, 0, s>>>(
+        img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr,
+        pair_counts);
     GSB_LAUNCH_CHECK();
     return 0;
 }

@@ -9,6 +9,13 @@
 // 4*odd floats so the per-thread 128-bit row reads are bank-conflict free.
 #include "gsb_common.cuh"
 
+static int gsb_sm_count_sh() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
 namespace {
 
 constexpr int SH_THREADS = 128;
@@ -177,42 +184,110 @@ sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs
 // reading the peers' v_rgb_r directly over NVLink (P2P loads on mapped pointers) while it computes; the
 // rank-1 structure of the SH VJP makes the local expansion exact.  NVLink traffic per rank drops from
 // 2(G-1)/G x 192 B to (G-1) x 12 B per Gaussian and the separate sh_backward pass disappears.
+// A CTA pulls each view's 1536-B span of its 128 Gaussians with fully coalesced loads (a warp request is one
+// contiguous 128-B line of the peer's memory) into shared memory, all views of a batch in flight at once, then
+// every thread expands its own Gaussian.
+//
+// The same launch also carries the all-reduce of the remaining per-Gaussian gradients (means, scales, quats,
+// opacity: the `geom` prefix of the flat gradient buffer, 44 B/Gaussian): the first `geom_blocks` CTAs run a
+// two-shot all-reduce in which rank r owns slice r -- with NVSwitch multicast (`geom_mc` != NULL) one
+// multimem.ld_reduce pulls the sum of all ranks' copies through the switch and one multimem.st broadcasts the
+// result to every rank; without multicast the slice is summed from / written to the peers' mapped pointers.
+// The caller brackets the launch with two cross-rank barriers (inputs complete / results visible).
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float *mc_ptr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float *mc_ptr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(mc_ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr int MV_MAX_RANKS = 16;   // peers the non-multicast all-reduce role can address
+
 template <int K>
 __global__ void __launch_bounds__(SH_THREADS)
 sh_backward_multiview_kernel(int n, int degrees_to_use, const float *__restrict__ means, int num_views,
                              const float *__restrict__ cam_pos, const float *const *__restrict__ v_rgb_views,
-                             float scale, float *__restrict__ v_coeffs, int vec_ok) {
+                             float scale, float *__restrict__ v_coeffs, int vec_ok,
+                             // ---- all-reduce role (geom_blocks == 0: none) ----
+                             int geom_blocks, int rank, int world, long long geom_vec4,
+                             float *const *__restrict__ geom_ranks, float *geom_mc) {
     constexpr int C = 3 * K;
     constexpr int S = sh_row_stride(K);
+    constexpr int VB = (K > 16) ? 4 : 8;   // views staged per batch (48-KB static shared-memory budget)
+    if ((int)blockIdx.x < geom_blocks) {
+        // ---- role B: two-shot all-reduce of this rank's slice of the geometry gradients ----
+        const long long chunk = (geom_vec4 + world - 1) / world;
+        const long long lo = chunk * rank, hi = min(geom_vec4, lo + chunk);
+        const long long stride = (long long)geom_blocks * SH_THREADS;
+        if (geom_mc != nullptr) {
+            for (long long i = lo + (long long)blockIdx.x * SH_THREADS + threadIdx.x; i < hi; i += stride) {
+                float4 v = multimem_ld_reduce_add(geom_mc + 4 * i);
+                v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                multimem_st(geom_mc + 4 * i, v);
+            }
+        } else {
+            for (long long i = lo + (long long)blockIdx.x * SH_THREADS + threadIdx.x; i < hi; i += stride) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 part[MV_MAX_RANKS];
+#pragma unroll
+                for (int r = 0; r < MV_MAX_RANKS; ++r)
+                    if (r < world) part[r] = *(reinterpret_cast<const float4 *>(geom_ranks[r]) + i);
+#pragma unroll
+                for (int r = 0; r < MV_MAX_RANKS; ++r)
+                    if (r < world) { acc.x += part[r].x; acc.y += part[r].y; acc.z += part[r].z; acc.w += part[r].w; }
+                acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+#pragma unroll
+                for (int r = 0; r < MV_MAX_RANKS; ++r)
+                    if (r < world) *(reinterpret_cast<float4 *>(geom_ranks[r]) + i) = acc;
+            }
+        }
+        return;
+    }
+    // ---- role A: multi-view SH VJP with peer pulls ----
     __shared__ __align__(16) float tile[SH_THREADS * S];
-    const int g0 = blockIdx.x * SH_THREADS;
+    __shared__ float stage[VB][3 * SH_THREADS];
+    const int blk = (int)blockIdx.x - geom_blocks;
+    const int g0 = blk * SH_THREADS;
     const int ng = min(SH_THREADS, n - g0);
     const int nb = min(nb_of(degrees_to_use), K);
     const int t = threadIdx.x;
-    if (t < ng) {
-        const int g = g0 + t;
-        const float mx = means[3 * g], my = means[3 * g + 1], mz = means[3 * g + 2];
-        float row[S];
+    const int g = g0 + t;
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (t < ng) { mx = means[3 * g]; my = means[3 * g + 1]; mz = means[3 * g + 2]; }
+    float row[S];
 #pragma unroll
-        for (int j = 0; j < S; ++j) row[j] = 0.f;
-        // views are processed in groups of 8 whose (peer, NVLink) loads are all issued before any use:
-        // remote-load latency (~2-3 us) is paid once per group, not once per view
-        for (int r0 = 0; r0 < num_views; r0 += 8) {
-            float vv[8][3];
+    for (int j = 0; j < S; ++j) row[j] = 0.f;
+    const int span = 3 * ng;                     // floats of one view's colour-gradient span of this CTA
+    for (int r0 = 0; r0 < num_views; r0 += VB) {
+        // coalesced pull: thread t takes floats t, t+128, t+256 of every view's span; all loads of the batch are
+        // issued before the first use, so the (NVLink) latency is paid once per batch
+        float pull[VB][3];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                vv[u][0] = vv[u][1] = vv[u][2] = 0.f;
-                if (r0 + u < num_views) {
-                    const float *vr = v_rgb_views[r0 + u];  // local or peer-mapped (NVLink) pointer
-                    vv[u][0] = vr[3 * g];
-                    vv[u][1] = vr[3 * g + 1];
-                    vv[u][2] = vr[3 * g + 2];
-                }
+        for (int u = 0; u < VB; ++u) {
+            pull[u][0] = pull[u][1] = pull[u][2] = 0.f;
+            if (r0 + u < num_views) {
+                const float *vr = v_rgb_views[r0 + u] + (size_t)3 * g0;   // local or peer-mapped pointer
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (t + q * SH_THREADS < span) pull[u][q] = vr[t + q * SH_THREADS];
             }
+        }
+        __syncthreads();   // the previous batch has been consumed
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float v0 = vv[u][0], v1 = vv[u][1], v2 = vv[u][2];
-                if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;  // not visible in this view (or no view)
+        for (int u = 0; u < VB; ++u)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) stage[u][t + q * SH_THREADS] = pull[u][q];
+        __syncthreads();
+        if (t < ng) {
+#pragma unroll
+            for (int u = 0; u < VB; ++u) {
+                if (r0 + u >= num_views) break;
+                const float v0 = stage[u][3 * t], v1 = stage[u][3 * t + 1], v2 = stage[u][3 * t + 2];
+                if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;  // not visible in this view
                 const int r = r0 + u;
                 float Y[K];
                 sh_basis(nb, mx - __ldg(cam_pos + 3 * r), my - __ldg(cam_pos + 3 * r + 1),
@@ -227,6 +302,8 @@ sh_backward_multiview_kernel(int n, int degrees_to_use, const float *__restrict_
                 }
             }
         }
+    }
+    if (t < ng) {
 #pragma unroll
         for (int j = 0; j < S; j += 4)
             *reinterpret_cast<float4 *>(&tile[t * S + j]) =
@@ -238,13 +315,13 @@ sh_backward_multiview_kernel(int n, int degrees_to_use, const float *__restrict_
     if (vec_ok && (C % 4 == 0)) {
         float4 *dst4 = reinterpret_cast<float4 *>(dst);
         for (int f = threadIdx.x; f < total / 4; f += SH_THREADS) {
-            int e = 4 * f, g = e / C, j = e - g * C;
-            stg_stream4(dst4 + f, *reinterpret_cast<const float4 *>(&tile[g * S + j]));
+            int e = 4 * f, gg = e / C, j = e - gg * C;
+            stg_stream4(dst4 + f, *reinterpret_cast<const float4 *>(&tile[gg * S + j]));
         }
     } else {
         for (int e = threadIdx.x; e < total; e += SH_THREADS) {
-            int g = e / C, j = e - g * C;
-            dst[e] = tile[g * S + j];
+            int gg = e / C, j = e - gg * C;
+            dst[e] = tile[gg * S + j];
         }
     }
 }
@@ -346,18 +423,25 @@ extern "C" int gsb_mask_rgb_grad(int n, const float *rgbs, float *v_rgbs, gsb_st
     return 0;
 }
 
-extern "C" int gsb_sh_backward_multiview(int n, int degree, int degrees_to_use, const float *means,
-                                         int num_views, const float *cam_positions,
-                                         const float *const *v_rgbs_per_view, float scale, float *v_coeffs,
-                                         gsb_stream_t stream) {
+static int launch_multiview(int n, int degree, int degrees_to_use, const float *means, int num_views,
+                            const float *cam_positions, const float *const *v_rgbs_per_view, float scale,
+                            float *v_coeffs, int rank, int world, long long geom_floats, float *const *geom_per_rank,
+                            float *geom_multicast, gsb_stream_t stream) {
     GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
-    GSB_CHECK_ARG(num_views >= 1);
-    if (n == 0) return 0;
-    GSB_CHECK_ARG(means && cam_positions && v_rgbs_per_view && v_coeffs);
+    GSB_CHECK_ARG(num_views >= 1 && geom_floats >= 0);
+    int geom_blocks = 0;
+    if (geom_floats > 0) {
+        GSB_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (geom_floats % 4) == 0);
+        GSB_CHECK_ARG(geom_multicast || (geom_per_rank && world <= MV_MAX_RANKS));
+        GSB_CHECK_ARG(((uintptr_t)geom_multicast % 16) == 0);
+        geom_blocks = 2 * gsb_sm_count_sh();
+    }
+    if (n == 0 && geom_blocks == 0) return 0;
+    GSB_CHECK_ARG(n == 0 || (means && cam_positions && v_rgbs_per_view && v_coeffs));
     cudaStream_t s = (cudaStream_t)stream;
-    int grid = gsb_div_up(n, SH_THREADS);
+    int grid = geom_blocks + gsb_div_up(n, SH_THREADS);
     int vec_ok = ((uintptr_t)v_coeffs % 16) == 0;
-#define GSB_SH_M(K) sh_backward_multiview_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, means, num_views, cam_positions, v_rgbs_per_view, scale, v_coeffs, vec_ok)
+#define GSB_SH_M(K) sh_backward_multiview_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, means, num_views, cam_positions, v_rgbs_per_view, scale, v_coeffs, vec_ok, geom_blocks, rank, world, geom_floats / 4, geom_per_rank, geom_multicast)
     switch (degree) {
         case 0: GSB_SH_M(1); break;
         case 1: GSB_SH_M(4); break;
@@ -368,4 +452,20 @@ extern "C" int gsb_sh_backward_multiview(int n, int degree, int degrees_to_use, 
 #undef GSB_SH_M
     GSB_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int gsb_sh_backward_multiview(int n, int degree, int degrees_to_use, const float *means,
+                                         int num_views, const float *cam_positions,
+                                         const float *const *v_rgbs_per_view, float scale, float *v_coeffs,
+                                         gsb_stream_t stream) {
+    return launch_multiview(n, degree, degrees_to_use, means, num_views, cam_positions, v_rgbs_per_view, scale,
+                            v_coeffs, 0, 1, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int gsb_exchange_gradients(int n, int degree, int degrees_to_use, const float *means, int num_views,
+                                      const float *cam_positions, const float *const *v_rgbs_per_view, float scale,
+                                      float *v_coeffs, int rank, int world, long long geom_floats,
+                                      float *const *geom_per_rank, float *geom_multicast, gsb_stream_t stream) {
+    return launch_multiview(n, degree, degrees_to_use, means, num_views, cam_positions, v_rgbs_per_view, scale,
+                            v_coeffs, rank, world, geom_floats, geom_per_rank, geom_multicast, stream);
 }

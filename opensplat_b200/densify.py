@@ -29,6 +29,10 @@ class RefineConfig:
     cull_screen_size: float = 0.15
     size_fac: float = 1.6
     n_split_samples: int = 2        # fixed by the row map (kinds 1, 2)
+    # Alpha reset: the reference BUILDS a zeroed Adam state for the opacities and then drops it (model.cpp:477-486;
+    # DESIGN.md D14), so its moments effectively survive.  True = the evident intent (moments zeroed), False = the
+    # reference's effective behaviour (moments kept).
+    reset_opacity_moments: bool = True
 
     @property
     def stop_split_at(self):        # model.hpp:31
@@ -105,6 +109,12 @@ class Densifier:
         capi.check(fn(n, capi.ptr(v_xy), capi.ptr(radii), img_h, img_w, capi.ptr(self.xys_grad_norm),
                       capi.ptr(self.vis_counts), capi.ptr(self.max_2d_size), capi.stream()))
 
+    def _world(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
     def sync_stats(self, group=None):
         """Data-parallel replicas render different views, so their statistics differ; reduce them (sum of gradient
         norms and visibility counts, max of screen sizes) so that every replica classifies identically.  Device
@@ -134,7 +144,13 @@ class Densifier:
         c = self.cfg
         info = {"refined": False, "added": 0, "culled": 0, "alpha_reset": False, "n": int(radii.shape[0])}
         if v_xy is None:                      # `!xys.grad().defined()`  (radii.sum() == 0), model.cpp:315
-            return params, adam_m, adam_v, info
+            if self._world() <= 1:
+                return params, adam_m, adam_v, info
+            # Data-parallel: this rank's view saw nothing, but the other ranks will enter the collectives of a
+            # refine step and change the Gaussian count -- take the same branches with zero statistics instead of
+            # returning (a rank that skips would hang the all-reduce or keep a different Gaussian set).
+            v_xy = torch.zeros((radii.shape[0], 2), dtype=torch.float32, device=radii.device)
+            radii = torch.zeros_like(radii)
         if step < c.stop_split_at:
             self.accumulate(v_xy, radii, img_h, img_w)
         refine, densify, reset, chk_screen, chk_huge = self.schedule(step)
@@ -146,8 +162,9 @@ class Densifier:
             params, adam_m, adam_v, r = self.refine(params, adam_m, adam_v, max(img_h, img_w), chk_screen, chk_huge)
             info.update(r)
         if reset:
-            m = adam_m.get("opacities") if adam_m else None
-            v = adam_v.get("opacities") if adam_v else None
+            zero = self.cfg.reset_opacity_moments
+            m = adam_m.get("opacities") if (adam_m and zero) else None
+            v = adam_v.get("opacities") if (adam_v and zero) else None
             self.reset_opacity(params["opacities"], m, v)
             info["alpha_reset"] = True
         self.xys_grad_norm = self.vis_counts = self.max_2d_size = None   # "Clear", model.cpp:489-492
@@ -167,6 +184,12 @@ class Densifier:
             samples = self.sample_fn(c.n_split_samples * n_splits, d).to(device=d, dtype=torch.float32).contiguous()
         else:
             samples = torch.randn((c.n_split_samples * n_splits, 3), device=d, generator=self.generator)  # model.cpp:359
+            if self._world() > 1:
+                # replicas must place the split children identically: rank 0's draw is the one everybody uses
+                # (per-process generators are not synchronised; the reference is single-GPU)
+                import torch.distributed as dist
+                src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+                dist.broadcast(samples, src=src, group=self.group)
         new_p = {}
         new_p["means"], new_p["scales"] = means_scales(src_map, split_rank, new_n, n_splits, samples, params["means"],
                                                        params["scales"], params["quats"], c.size_fac)

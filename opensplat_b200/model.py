@@ -154,13 +154,17 @@ class GaussianModel:
 
     # ---- Model::afterTrain (model.cpp:311-500) ---------------------------------------------------------------
     def after_train(self, step):
-        if self.xys is None or self.xys.grad is None:
+        if self.xys is None:
+            return {"refined": False}
+        # xys.grad undefined <=> this view hit no Gaussian (model.cpp:315).  Single process: nothing to do.  Under a
+        # process group the densifier still has to take part in the refine step's collectives (zero statistics).
+        v_xy = self.xys.grad.detach().contiguous() if self.xys.grad is not None else None
+        if v_xy is None and self.densifier._world() <= 1:
             return {"refined": False}
         with torch.no_grad():
             p = {k: getattr(self, k).detach() for k in PARAM_NAMES}
             new_p, new_m, new_v, info = self.densifier.after_train(
-                step, p, self.adam_m, self.adam_v, self.xys.grad.detach().contiguous(), self.radii, self.lastHeight,
-                self.lastWidth)
+                step, p, self.adam_m, self.adam_v, v_xy, self.radii, self.lastHeight, self.lastWidth)
             if new_p is not p:
                 for k in PARAM_NAMES:
                     setattr(self, k, new_p[k].requires_grad_())

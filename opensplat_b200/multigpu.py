@@ -1,16 +1,24 @@
-"""Data-parallel (over camera views) gradient exchange on NVLink, fused with the SH backward pass.
+"""Data-parallel (over camera views) gradient exchange on NVLink / NVSwitch, fused with the SH backward pass.
 
 Baseline (parallel.allreduce_gradients): every rank runs sh_backward and then ONE NCCL all-reduce over the
 flat 59-float/Gaussian gradient buffer (236 MB at 1M Gaussians, SH degree 3).
 
-Fused path (this module): the SH VJP is rank-1 in (view basis) x (colour gradient), so instead of reducing the
-48 coefficient gradients per Gaussian, every rank exposes only its view's colour gradient v_rgb [N,3] in
-symmetric (peer-mapped) memory, and `gsb_sh_backward_multiview` forms sum_r Y_r (x) v_rgb_r itself, loading the
-peers' v_rgb over NVLink (P2P) while it computes.  The remaining 11 floats/Gaussian (means, scales, quats,
-opacity) go through one small NCCL all-reduce on a side stream, overlapped with the fused kernel.
-NVLink bytes per rank per step at G ranks: (G-1) x 12 B + 2(G-1)/G x 44 B per Gaussian instead of
-2(G-1)/G x 236 B (G = 8: 161 MB instead of 413 MB at 1M Gaussians), and one kernel fewer.
+Fused path (this module), ONE kernel launch per step (`gsb_exchange_gradients`) between two cross-rank barriers:
+ * the SH VJP is rank-1 in (view basis) x (colour gradient), so instead of reducing the 48 coefficient gradients
+   per Gaussian every rank exposes only its view's colour gradient v_rgb [N,3] in symmetric (peer-mapped) memory
+   and the kernel forms sum_r Y_r (x) v_rgb_r itself, pulling the peers' v_rgb over NVLink with coalesced loads
+   while it computes;
+ * the remaining 11 floats/Gaussian (means, scales, quats, opacity -- the prefix of the flat gradient buffer, which
+   lives in the same symmetric allocation so the backward kernels write it in place) are all-reduced by the first
+   CTAs of the same launch: two-shot, rank r owns slice r, with NVSwitch multicast one `multimem.ld_reduce` (sum
+   formed inside the switch) and one `multimem.st` (broadcast) per 16 bytes; without multicast through the peers'
+   mapped pointers.
+NVLink bytes per rank per step at G ranks (N Gaussians): received (G-1) x 12 N (colour gradients) + 44 N
+(reduced slice + broadcasts), sent the same -- against 2(G-1)/G x 236 N each way for the flat all-reduce
+(G = 8: 128 MB instead of 413 MB at 1M Gaussians), and no separate sh_backward / NCCL kernels.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -19,70 +27,63 @@ from . import capi
 
 class ViewParallelExchange:
     def __init__(self, pipe, cam_pos, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
         self.pipe = pipe
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         dev = pipe.dev
-        self._alloc_symmetric(pipe.n)
         # every rank's camera centre (tiny, exchanged once)
         cp = torch.as_tensor(cam_pos, dtype=torch.float32, device=dev).reshape(1, 3)
         allcp = [torch.zeros_like(cp) for _ in range(self.world)]
         dist.all_gather(allcp, cp, group=self.group)
         self.cam_positions = torch.cat(allcp, 0).contiguous()
-        self.side = torch.cuda.Stream(device=dev)
-        assert pipe.sizes[-1][0] == "coeffs"
+        self.use_multicast = os.environ.get("GSB_EXCHANGE_MULTICAST", "1") != "0"
+        self._alloc_symmetric(pipe)
 
-    def _alloc_symmetric(self, n):
+    def _alloc_symmetric(self, pipe):
         import torch.distributed._symmetric_memory as symm_mem
-        dev = self.pipe.dev
-        # two symmetric buffers (double-buffered so ONE barrier per step is enough, see exchange())
-        self.bufs, self.hdls, self.ptrs = [], [], []
-        for _ in range(2):
-            t = symm_mem.empty((n, 3), dtype=torch.float32, device=dev)
-            t.zero_()
-            h = symm_mem.rendezvous(t, self.group.group_name)
-            self.bufs.append(t)
-            self.hdls.append(h)
-            self.ptrs.append(h.buffer_ptrs_dev)  # device array of world_size pointers (peer-mapped)
-        self.step = 0
-        self.geom_numel = n * 11  # means 3 + scales 3 + quats 4 + opacity 1: the prefix of the flat buffer
+        dev, n = pipe.dev, pipe.n
+        # ONE symmetric allocation: [flat gradient buffer | this view's colour gradient v_rgb [n,3]]
+        rgb_off = (pipe.numel + 3) // 4 * 4
+        total = rgb_off + (3 * n + 3) // 4 * 4
+        t = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        t.zero_()
+        hdl = symm_mem.rendezvous(t, self.group.group_name)
+        self.buf, self.hdl = t, hdl
+        pipe.rebind_grad_flat(t[:pipe.numel])
+        self.v_rgb = t[rgb_off:rgb_off + 3 * n].view(n, 3)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.geom_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)              # peers' flat buffers
+        self.rgb_ptrs = torch.tensor([p + 4 * rgb_off for p in ptrs], dtype=torch.int64, device=dev)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if self.use_multicast else 0
+        self.multicast_ptr = mc                                                           # 0: no NVSwitch multicast
+        self.geom_numel = pipe.geom_numel   # means, scales, quats, opacities (16-byte aligned slices)
+        assert self.geom_numel % 4 == 0
 
     def resize(self, pipe):
         """After a refinement changed the Gaussian count (collective: every rank refines in lock-step, see
         densify.Densifier.sync_stats): new symmetric buffers + rendezvous."""
         torch.cuda.current_stream().synchronize()
         dist.barrier(group=self.group)
-        self._alloc_symmetric(pipe.n)
+        self._alloc_symmetric(pipe)
 
     def v_rgbs_buffer(self):
         """Where this step's rasterize-backward must write its colour gradient."""
-        return self.bufs[self.step % 2]
+        return self.v_rgb
 
     def exchange(self, average=True):
-        """Call after project_backward: masks v_rgbs, synchronises the ranks, runs the fused multi-view SH
-        backward (peer loads over NVLink) and, concurrently, the NCCL all-reduce of the geometry gradients."""
+        """Call after project_backward: masks v_rgb with the clamp's gradient, then one fused launch does the
+        multi-view SH backward (peer pulls over NVLink) and the all-reduce of the geometry gradients."""
         p = self.pipe
         L = capi.lib()
-        i = self.step % 2
-        buf, hdl = self.bufs[i], self.hdls[i]
-        cur = torch.cuda.current_stream()
         scale = 1.0 / self.world if average else 1.0
-        # geometry gradients: small NCCL all-reduce on a side stream, overlapped with the fused kernel
-        geom = p.grad_flat[: self.geom_numel]
-        self.side.wait_stream(cur)
-        with torch.cuda.stream(self.side):
-            dist.all_reduce(geom, op=dist.ReduceOp.SUM, group=self.group)
-            if average:
-                geom.mul_(scale)
-        capi.check(L.gsb_mask_rgb_grad(p.n, capi.ptr(p.rgbs), capi.ptr(buf), capi.stream()))
-        # all ranks have finished writing this step's v_rgbs.  (Double buffering: the buffer written at step
-        # t is last READ by peers in step t's fused kernel, which every rank has passed in stream order
-        # before it reaches the barrier of step t+1, i.e. before anyone writes that buffer again at t+2.)
-        hdl.barrier(channel=0)
-        capi.check(L.gsb_sh_backward_multiview(p.n, p.deg, p.deg, capi.ptr(p.p["means"]), self.world,
-                                               capi.ptr(self.cam_positions), self.ptrs[i], scale,
-                                               capi.ptr(p.g["coeffs"]), capi.stream()))
-        cur.wait_stream(self.side)
-        self.step += 1
+        capi.check(L.gsb_mask_rgb_grad(p.n, capi.ptr(p.rgbs), capi.ptr(self.v_rgb), capi.stream()))
+        # every rank has finished writing this step's v_rgb and geometry gradients
+        self.hdl.barrier(channel=0)
+        capi.check(L.gsb_exchange_gradients(
+            p.n, p.deg, p.deg, capi.ptr(p.p["means"]), self.world, capi.ptr(self.cam_positions),
+            self.rgb_ptrs.data_ptr(), scale, capi.ptr(p.g["coeffs"]), self.rank, self.world, self.geom_numel,
+            self.geom_ptrs.data_ptr(), self.multicast_ptr if self.multicast_ptr else None, capi.stream()))
+        # every rank's slice of the reduced geometry gradients has landed everywhere, and nobody still reads the
+        # v_rgb / geometry buffers of this step (so the next backward pass may overwrite them)
+        self.hdl.barrier(channel=0)

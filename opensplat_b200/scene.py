@@ -77,3 +77,35 @@ def rotated_camera(W, H, k, n_views=8, t_z=8.0):
     cam["projmat"] = view.copy()
     cam["cam_pos"] = (-R.T @ np.array([0, 0, t_z], np.float32)).astype(np.float32)
     return cam
+
+
+# The 8 data-parallel views of config C4.  The synthetic scene fills the cube [-1,1]^3 uniformly, so the rotations of
+# the cube's symmetry group map it onto itself: every view below sees the same footprint on screen (the whole
+# image), the same depth range and, statistically, the same number of intersections -- ranks of a weak-scaling run
+# then carry comparable work, and N-GPU throughput can be compared with N x the 1-GPU number.  (Generic orbit
+# views, rotated_camera(), crop the cube differently per view and skew the per-rank work by up to ~25 %.)
+_CUBE_VIEWS = [
+    np.eye(3),                                      # 0: front (the single-GPU view)
+    [[0, 0, 1], [0, 1, 0], [-1, 0, 0]],             # 1: 90 deg about y
+    [[-1, 0, 0], [0, 1, 0], [0, 0, -1]],            # 2: 180 deg about y (back)
+    [[0, 0, -1], [0, 1, 0], [1, 0, 0]],             # 3: 270 deg about y
+    [[1, 0, 0], [0, 0, -1], [0, 1, 0]],             # 4: 90 deg about x (top)
+    [[1, 0, 0], [0, 0, 1], [0, -1, 0]],             # 5: 270 deg about x (bottom)
+    [[0, -1, 0], [1, 0, 0], [0, 0, 1]],             # 6: front, rolled 90 deg
+    [[0, 1, 0], [1, 0, 0], [0, 0, -1]],             # 7: back, rolled (180 deg about the x=y diagonal)
+]
+
+
+def cube_view_camera(W, H, k, t_z=8.0):
+    """View k (mod 8) of the C4 view set: a rotation of the cube's symmetry group applied to the scene, camera
+    convention as make_camera (projmat = viewmat, w == 1)."""
+    cam = make_camera(W, H, t_z)
+    R = np.asarray(_CUBE_VIEWS[k % 8], np.float32)
+    assert abs(float(np.linalg.det(R)) - 1.0) < 1e-6
+    view = np.eye(4, dtype=np.float32)
+    view[:3, :3] = R
+    view[2, 3] = t_z
+    cam["viewmat"] = view
+    cam["projmat"] = view.copy()
+    cam["cam_pos"] = (-R.T @ np.array([0, 0, t_z], np.float32)).astype(np.float32)
+    return cam

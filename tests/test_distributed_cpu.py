@@ -114,3 +114,57 @@ def test_separate_tensor_gradients_one_bucket_world2():
     mp.spawn(_grads_worker, args=(world, port, ret), nprocs=world, join=True)
     for r in (0, 1):
         assert np.all(ret[r][0] == 1.5) and np.all(ret[r][1] == 15.0) and np.all(ret[r][2] == 2.5)
+
+
+def _lockstep_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from opensplat_b200.densify import Densifier, RefineConfig
+
+    class HostDensifier(Densifier):
+        """The control flow of Densifier.after_train with the two device calls replaced by host arithmetic."""
+        def accumulate(self, v_xy, radii, img_h, img_w):
+            n = radii.shape[0]
+            if self.xys_grad_norm is None:
+                self.xys_grad_norm, self.vis_counts, self.max_2d_size = torch.zeros(n), torch.zeros(n), torch.zeros(n)
+            vis = radii > 0
+            self.xys_grad_norm += v_xy.norm(dim=-1) * vis
+            self.vis_counts += vis.float()
+
+        def refine(self, params, adam_m, adam_v, max_dim, check_split_screen, check_huge):
+            # the decision every replica must agree on: Gaussians whose reduced gradient statistic is large
+            keep = (self.xys_grad_norm / self.vis_counts.clamp_min(1)) < 0.5
+            newp = {k: v[keep] for k, v in params.items()}
+            return newp, adam_m, adam_v, {"n": int(keep.sum()), "added": 0, "culled": int((~keep).sum())}
+
+        def reset_opacity(self, opacities, exp_avg=None, exp_avg_sq=None):
+            opacities.clamp_(max=-1.0)
+
+    cfg = RefineConfig(refine_every=2, warmup_length=1, num_cameras=0, reset_alpha_every=1000)
+    dn = HostDensifier(cfg)
+    n = 64
+    params = {"means": torch.arange(n * 3, dtype=torch.float32).view(n, 3), "opacities": torch.zeros(n, 1)}
+    g = torch.Generator().manual_seed(5)
+    counts = []
+    for step in range(1, 7):
+        # rank 1's view never hits a Gaussian: its xys.grad is undefined (v_xy None) on every step
+        v_xy = torch.rand(params["means"].shape[0], 2, generator=g) if rank == 0 else None
+        radii = torch.ones(params["means"].shape[0], dtype=torch.int32)
+        params, _, _, info = dn.after_train(step, params, None, None, v_xy, radii, 100, 100)
+        counts.append(params["means"].shape[0])
+    ret[rank] = (counts, params["means"].numpy().copy())
+    dist.destroy_process_group()
+
+
+def test_refinement_stays_in_lockstep_when_one_rank_sees_nothing_world2():
+    """a rank whose view hits no Gaussian must still take part in the refine step's collectives and end up
+    with the same Gaussian set as the others (no hang, no divergence)."""
+    import numpy as np
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_lockstep_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] == ret[1][0] and ret[0][0][-1] < 64          # both replicas culled the same Gaussians
+    assert np.array_equal(ret[0][1], ret[1][1])

@@ -1,7 +1,8 @@
-"""torchrun --nproc-per-node N tools/check_multigpu.py : data-parallel correctness on N GPUs.
-Checks that the fused exchange (multi-view SH backward over peer memory + small NCCL all-reduce) produces
-the same averaged gradients as sh_backward + one NCCL all-reduce of the whole flat buffer, and that
-replicas stay bit-identical after Adam steps."""
+"""torchrun --nproc-per-node N tools/check_multigpu.py [--no-resize] : data-parallel correctness on N GPUs.
+Checks that the fused exchange launch (multi-view SH backward over peer memory + two-shot all-reduce of the geometry
+gradients, NVSwitch multimem when available; GSB_EXCHANGE_MULTICAST=0 forces the peer-pointer flavour) produces the
+same averaged gradients as sh_backward + one NCCL all-reduce of the whole flat buffer, that replicas stay
+bit-identical after Adam steps, and that both still hold after a lock-step change of the Gaussian count."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -38,30 +39,37 @@ parallel.allreduce_gradients(a.grad_flat, world, average=True)
 # fused exchange
 b = make_pipe()
 b.exchange = ViewParallelExchange(b, cam["cam_pos"])
-for _ in range(3):   # several steps: exercises the double buffering
+for _ in range(3):   # several steps: the symmetric buffers are reused every step
     b.forward(); b.backward()
 torch.cuda.synchronize()
-ga, gb = a.grad_flat, b.grad_flat
-geo = n * 11
-err_geo = float((ga[:geo] - gb[:geo]).abs().max())
-rel_sh = float((ga[geo:] - gb[geo:]).norm() / ga[geo:].norm())
-ok = err_geo == 0.0 and rel_sh < 1e-5
+
+
+def compare(ref, got, geo):
+    """geometry prefix: same sums in a possibly different order (exact at world 2, where the order cannot matter);
+    SH block: expanded from the exchanged colour gradients instead of reduced -> fp32 re-association only."""
+    d = (ref[:geo] - got[:geo])
+    e_geo = float(d.abs().max())
+    r_geo = float(d.norm() / ref[:geo].norm())
+    r_sh = float((ref[geo:] - got[geo:]).norm() / ref[geo:].norm())
+    good = (e_geo == 0.0 if world <= 2 else r_geo < 1e-6) and r_sh < 1e-5
+    return good, e_geo, r_sh
+
+
+ok, err_geo, rel_sh = compare(a.grad_flat, b.grad_flat, b.geom_numel)
+mc = bool(b.exchange.multicast_ptr)
 # replicas stay identical through training steps
 for _ in range(3):
     b.train_step(world_size=world)
 sync = parallel.replicas_in_sync(b.param_flat, world)
 # a refinement changes the Gaussian count on every replica in lock-step (densify.Densifier.sync_stats makes the
 # decisions identical): new flat layout + new symmetric buffers, and the fused exchange keeps matching plain NCCL
-do_resize = "--resize" in sys.argv
+do_resize = "--no-resize" not in sys.argv
 ok2 = True
 if do_resize:
     keep = torch.arange(0, n, 2, device=dev)
-    idx = torch.cat([keep, keep[:1000]])
-    o, views_m, views_v = 0, {}, {}
-    for name, shp in b.sizes:
-        c = int(torch.Size(shp).numel())
-        views_m[name], views_v[name] = b.adam_m[o:o + c].view(shp), b.adam_v[o:o + c].view(shp)
-        o += c
+    idx = torch.cat([keep, keep[:1001]])     # odd count: the aligned flat layout must cope
+    views_m = {name: b.adam_m[o:o + c].view(shp) for name, (o, c, shp) in b.offs.items()}
+    views_v = {name: b.adam_v[o:o + c].view(shp) for name, (o, c, shp) in b.offs.items()}
     newp = {k: v[idx].clone() for k, v in b.p.items()}
     newm = {k: v[idx].clone() for k, v in views_m.items()}
     newv = {k: v[idx].clone() for k, v in views_v.items()}
@@ -78,10 +86,7 @@ if do_resize:
     c.forward(); c.backward()
     parallel.allreduce_gradients(c.grad_flat, world, average=True)
     torch.cuda.synchronize()
-    geo2 = b.n * 11
-    e_geo2 = float((c.grad_flat[:geo2] - b.grad_flat[:geo2]).abs().max())
-    r_sh2 = float((c.grad_flat[geo2:] - b.grad_flat[geo2:]).norm() / c.grad_flat[geo2:].norm())
-    ok2 = e_geo2 == 0.0 and r_sh2 < 1e-5
+    ok2, e_geo2, r_sh2 = compare(c.grad_flat, b.grad_flat, b.geom_numel)
     if rank == 0:
         print(f"after resize to n={b.n}: geometry max|d|={e_geo2:.3g} sh rel-L2={r_sh2:.3g}")
     b.train_step(world_size=world)
@@ -90,7 +95,7 @@ ok = ok and ok2
 res = torch.tensor([int(ok), int(sync)], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"multigpu check world={world}: geometry max|d|={err_geo:.3g} sh rel-L2={rel_sh:.3g} after_resize_ok={ok2} "
+    print(f"multigpu check world={world} multicast={mc}: geometry max|d|={err_geo:.3g} sh rel-L2={rel_sh:.3g} after_resize_ok={ok2} "
           f"fused_ok={bool(res[0])} replicas_in_sync={bool(res[1])}")
 dist.destroy_process_group()
 sys.exit(0 if bool(res[0]) and bool(res[1]) else 1)
