@@ -283,9 +283,36 @@ def run_ours(args):
     n, W, H, scale, opac = WORKLOADS[args.workload]
     pipe, sc, cam, target_host = _setup_pipe(args.workload, dev, rank, world)
     fused = world > 1 and args.exchange == "fused"
+    exchange_check = None
     if fused:
-        from opensplat_b200.multigpu import ViewParallelExchange
-        pipe.exchange = ViewParallelExchange(pipe, cam["cam_pos"])
+        # The fused exchange is verified ONCE, outside every timed region, against the plain path (sh_backward +
+        # one NCCL all-reduce of the flat buffer) on this very scene; if it cannot be set up or disagrees, every rank
+        # falls back to the NCCL exchange and the line says so.
+        ok_local, geo_rel, sh_rel, why = 1, None, None, None
+        try:
+            from opensplat_b200.multigpu import ViewParallelExchange
+            pipe.exchange = ViewParallelExchange(pipe, cam["cam_pos"])
+            pipe.forward(); pipe.backward()
+            got = pipe.grad_flat.clone()
+            ex, pipe.exchange = pipe.exchange, None
+            pipe.forward(); pipe.backward()
+            dist.all_reduce(pipe.grad_flat, op=dist.ReduceOp.SUM)
+            ref = pipe.grad_flat * (1.0 / world)
+            pipe.exchange = ex
+            geo = pipe.geom_numel
+            geo_rel = float((ref[:geo] - got[:geo]).norm() / ref[:geo].norm())
+            sh_rel = float((ref[geo:] - got[geo:]).norm() / ref[geo:].norm())
+            ok_local = int(geo_rel < 1e-5 and sh_rel < 1e-4)
+            del got, ref
+        except Exception as exn:   # e.g. symmetric memory / multicast not available on this box
+            ok_local, why = 0, str(exn)[:200]
+        flag = torch.tensor([ok_local], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_check = {"verified_against_nccl": bool(flag[0]), "geometry_rel_l2": geo_rel, "sh_rel_l2": sh_rel,
+                          "multicast": bool(getattr(pipe.exchange, "multicast_ptr", 0)), "error": why}
+        if not bool(flag[0]):
+            pipe.exchange = None
+            fused = False
 
     def step_fwd_bwd():
         pipe.forward()
@@ -476,6 +503,7 @@ def run_ours(args):
         "roofline": roof, "roofline_path": roof_path,
         "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
         "per_rank": per_rank,
+        "exchange_check": exchange_check,
         "other_configs": side or None,
         "cpu_baseline": cpu,
     }

@@ -65,6 +65,18 @@ int gsb_sh_forward_rgb(int n, int degree, int degrees_to_use, const float *viewd
 int gsb_sh_backward_rgb(int n, int degree, int degrees_to_use, const float *viewdirs, const float *rgbs,
                         const float *v_rgbs, float *v_coeffs, gsb_stream_t stream);
 
+/* Split variants: the whole colour pass of Model::forward without its ATen glue --
+ * viewdirs = means - cam_pos (cam_pos: device float[3]; normalised inside, no gradient, model.cpp:176-177),
+ * coeffs = cat(features_dc [n,3], features_rest [n,K-1,3]) (model.cpp:186-188) read where they lie,
+ * rgbs = clamp_min(SH + bias, 0) (:192); the backward writes v_features_dc / v_features_rest directly (bases above
+ * degrees_to_use get 0).  features_rest / v_features_rest may be NULL at degree 0. */
+int gsb_sh_forward_split(int n, int degree, int degrees_to_use, const float *means, const float *cam_pos,
+                         const float *features_dc, const float *features_rest, float bias, float *rgbs,
+                         gsb_stream_t stream);
+int gsb_sh_backward_split(int n, int degree, int degrees_to_use, const float *means, const float *cam_pos,
+                          const float *rgbs, const float *v_rgbs, float *v_features_dc, float *v_features_rest,
+                          gsb_stream_t stream);
+
 /* Data-parallel training: SH VJP fused with the cross-GPU gradient exchange.
  * gsb_mask_rgb_grad: v_rgbs *= [rgbs > 0] in place (gradient of the clamp, done before exposing v_rgbs).
  * gsb_sh_backward_multiview: v_coeffs[g] = scale * sum_r Y(normalize(means[g] - cam_positions[r])) (x)

@@ -22,6 +22,8 @@ _SIGS = {
     "gsb_sh_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "gsb_sh_forward_rgb": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "gsb_sh_backward_rgb": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_sh_forward_split": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
+    "gsb_sh_backward_split": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_mask_rgb_grad": (_i, [_i, _vp, _vp, _vp]),
     "gsb_sh_backward_multiview": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp]),
     "gsb_exchange_gradients": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _i, C.c_longlong, _vp, _vp, _vp]),

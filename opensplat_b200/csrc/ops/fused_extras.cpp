@@ -32,6 +32,91 @@ torch::autograd::tensor_list MainLoss::backward(torch::autograd::AutogradContext
     return {v * grad_outputs[0], torch::Tensor(), torch::Tensor()};
 }
 
+namespace {
+int degFromBases(int64_t k) {   // spherical_harmonics.cpp:3-16
+    switch (k) {
+        case 1: return 0;
+        case 4: return 1;
+        case 9: return 2;
+        case 16: return 3;
+        default: return 4;
+    }
+}
+torch::Tensor orZeros(const torch::Tensor &g, const torch::Tensor &like_) {
+    return g.defined() ? f32(g) : torch::zeros_like(like_);
+}
+}  // namespace
+
+torch::autograd::tensor_list ActivateGaussians::forward(torch::autograd::AutogradContext *ctx, torch::Tensor means,
+                                                        torch::Tensor logScales, torch::Tensor rawQuats,
+                                                        torch::Tensor opacityLogits, torch::Tensor camPos) {
+    c10::cuda::CUDAGuard guard(means.device());
+    const int n = (int)means.size(0);
+    torch::Tensor m = f32(means), ls = f32(logScales), rq = f32(rawQuats), ol = f32(opacityLogits).reshape({-1});
+    torch::Tensor cp = camPos.to(means.device(), torch::kFloat32).reshape({3}).contiguous();
+    torch::Tensor scales = torch::empty_like(ls), quats = torch::empty_like(rq);
+    torch::Tensor opac = torch::empty({n, 1}, like(m, torch::kFloat32)), vd = torch::empty_like(m);
+    check(gsb_activate_forward(n, fp(m), fp(ls), fp(rq), fp(ol), fp(cp), fpw(scales), fpw(quats), fpw(opac), fpw(vd),
+                               stream()),
+          "gsb_activate_forward");
+    ctx->save_for_backward({scales, rq, opac});
+    ctx->mark_non_differentiable({vd});
+    return {scales, quats, opac, vd};
+}
+
+torch::autograd::tensor_list ActivateGaussians::backward(torch::autograd::AutogradContext *ctx,
+                                                         torch::autograd::tensor_list g) {
+    auto saved = ctx->get_saved_variables();
+    torch::Tensor scales = saved[0], rq = saved[1], opac = saved[2];
+    c10::cuda::CUDAGuard guard(scales.device());
+    const int n = (int)scales.size(0);
+    torch::Tensor vS = orZeros(g[0], scales), vQ = orZeros(g[1], rq), vO = orZeros(g[2], opac);
+    torch::Tensor vLs = torch::empty_like(scales), vRq = torch::empty_like(rq), vOl = torch::empty_like(opac);
+    check(gsb_activate_backward(n, fp(scales), fp(rq), fp(opac), fp(vS), fp(vQ), fp(vO), fpw(vLs), fpw(vRq), fpw(vOl),
+                                stream()),
+          "gsb_activate_backward");
+    return {torch::Tensor(), vLs, vRq, vOl, torch::Tensor()};
+}
+
+torch::Tensor SphericalHarmonicsRgb::forward(torch::autograd::AutogradContext *ctx, int64_t degreesToUse,
+                                             torch::Tensor means, torch::Tensor camPos, torch::Tensor featuresDc,
+                                             torch::Tensor featuresRest) {
+    c10::cuda::CUDAGuard guard(means.device());
+    const int n = (int)means.size(0);
+    const int degree = degFromBases(featuresRest.size(-2) + 1);
+    TORCH_CHECK(featuresDc.dim() == 2 && featuresDc.size(1) == 3 && featuresRest.dim() == 3 &&
+                    featuresRest.size(2) == 3 && featuresRest.size(0) == n,
+                "SphericalHarmonicsRgb: featuresDc [N,3], featuresRest [N,K-1,3]");
+    TORCH_CHECK(degreesToUse >= 0 && degreesToUse <= degree, "SphericalHarmonicsRgb: degreesToUse out of range");
+    torch::Tensor m = f32(means), dc = f32(featuresDc), rest = f32(featuresRest);
+    torch::Tensor cp = camPos.to(means.device(), torch::kFloat32).reshape({3}).contiguous();
+    torch::Tensor rgbs = torch::empty({n, 3}, like(m, torch::kFloat32));
+    check(gsb_sh_forward_split(n, degree, (int)degreesToUse, fp(m), fp(cp), fp(dc), fp(rest), 0.5f, fpw(rgbs),
+                               stream()),
+          "gsb_sh_forward_split");
+    ctx->saved_data["degreesToUse"] = degreesToUse;
+    ctx->saved_data["degree"] = (int64_t)degree;
+    ctx->saved_data["restBases"] = featuresRest.size(-2);
+    ctx->save_for_backward({m, cp, rgbs});
+    return rgbs;
+}
+
+torch::autograd::tensor_list SphericalHarmonicsRgb::backward(torch::autograd::AutogradContext *ctx,
+                                                             torch::autograd::tensor_list g) {
+    auto saved = ctx->get_saved_variables();
+    torch::Tensor m = saved[0], cp = saved[1], rgbs = saved[2];
+    c10::cuda::CUDAGuard guard(m.device());
+    const int n = (int)m.size(0);
+    const int degree = (int)ctx->saved_data["degree"].toInt();
+    torch::Tensor v = f32(g[0]);
+    torch::Tensor vDc = torch::empty({n, 3}, like(m, torch::kFloat32));
+    torch::Tensor vRest = torch::empty({n, ctx->saved_data["restBases"].toInt(), 3}, like(m, torch::kFloat32));
+    check(gsb_sh_backward_split(n, degree, (int)ctx->saved_data["degreesToUse"].toInt(), fp(m), fp(cp), fp(rgbs), fp(v),
+                                fpw(vDc), fpw(vRest), stream()),
+          "gsb_sh_backward_split");
+    return {torch::Tensor(), torch::Tensor(), torch::Tensor(), vDc, vRest};
+}
+
 void adamStep(torch::Tensor param, const torch::Tensor &grad, torch::Tensor expAvg, torch::Tensor expAvgSq, double lr,
               int64_t step, double beta1, double beta2, double eps) {
     TORCH_CHECK(param.is_cuda() && param.is_contiguous() && param.scalar_type() == torch::kFloat32,

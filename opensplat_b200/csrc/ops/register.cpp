@@ -50,7 +50,19 @@ static void op_densify_stats(torch::Tensor xysGrad, torch::Tensor radii, int64_t
     gsb::densifyStats(xysGrad, radii, (int)imgHeight, (int)imgWidth, first, xysGradNorm, visCounts, max2DSize);
 }
 
+static std::vector<torch::Tensor> op_activate(torch::Tensor means, torch::Tensor logScales, torch::Tensor rawQuats,
+                                              torch::Tensor opacityLogits, torch::Tensor camPos) {
+    return gsb::ActivateGaussians::apply(means, logScales, rawQuats, opacityLogits, camPos);
+}
+
+static torch::Tensor op_sh_rgb(int64_t degreesToUse, torch::Tensor means, torch::Tensor camPos, torch::Tensor featuresDc,
+                               torch::Tensor featuresRest) {
+    return gsb::SphericalHarmonicsRgb::apply(degreesToUse, means, camPos, featuresDc, featuresRest);
+}
+
 TORCH_LIBRARY(opensplat_b200, m) {
+    m.def("activate_gaussians", &op_activate);
+    m.def("spherical_harmonics_rgb", &op_sh_rgb);
     m.def("project_gaussians", &op_project);
     m.def("rasterize_gaussians", &op_rasterize);
     m.def("spherical_harmonics", &op_sh);

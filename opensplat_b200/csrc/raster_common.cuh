@@ -79,10 +79,10 @@ __device__ __forceinline__ GsbRecord make_record(float2 xy, float a, float b, fl
 __device__ __forceinline__ unsigned extent_slot_mask(float cx, float cy, float hx, float hy, float tile_x0,
                                                      float tile_y0) {
     const float gx = cx - tile_x0, gy = cy - tile_y0;   // centre in tile-local pixel coords
-    // pixel centres of the tile are 0..15 in both axes
-    const bool hit_x = (gx + hx >= 0.f) && (gx - hx <= 15.f);
+    // pixel centres of the tile are 0..15 in both axes: at least one integer column and row inside the extent
+    const float xlo = fmaxf(ceilf(gx - hx), 0.f), xhi = fminf(floorf(gx + hx), 15.f);
     const float ylo = fmaxf(ceilf(gy - hy), 0.f), yhi = fminf(floorf(gy + hy), 15.f);
-    if (!hit_x || !(ylo <= yhi)) return 0u;
+    if (!(xlo <= xhi) || !(ylo <= yhi)) return 0u;
     const int jlo = (int)ylo >> 1, jhi = (int)yhi >> 1;
     return ((2u << jhi) - 1u) & ~((1u << jlo) - 1u);
 }

@@ -239,6 +239,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
     }
 }
 
+
 }  // namespace
 
 int gsb_sm_count();

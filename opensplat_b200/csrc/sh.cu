@@ -70,7 +70,11 @@ template <int K>
 __global__ void __launch_bounds__(SH_THREADS)
 sh_forward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
                   const float *__restrict__ coeffs, float *__restrict__ colors, int vec_ok, int fuse_rgb,
-                  float bias) {
+                  float bias,
+                  // split inputs (gsb_sh_forward_split): coeffs = features_dc [n,3], rest = features_rest [n,K-1,3]
+                  // (the two tensors Model::forward concatenates, model.cpp:186-188); cam_pos != NULL: `viewdirs`
+                  // holds the MEANS and the direction means - cam_pos is formed here (model.cpp:176-177)
+                  int split, const float *__restrict__ rest, const float *__restrict__ cam_pos) {
     constexpr int C = 3 * K;
     constexpr int S = sh_row_stride(K);
     __shared__ __align__(16) float tile[SH_THREADS * S];
@@ -80,7 +84,15 @@ sh_forward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
     const float *src = coeffs + (size_t)g0 * C;
     const int total = ng * C;
     // ---- coalesced span load -> padded rows ----
-    if (vec_ok && (C % 4 == 0)) {
+    if (split) {
+        const float *dc = coeffs + (size_t)g0 * 3, *rs = rest + (size_t)g0 * (C - 3);
+        for (int e = threadIdx.x; e < ng * 3; e += SH_THREADS) tile[(e / 3) * S + (e % 3)] = __ldg(dc + e);
+        if (C > 3)
+            for (int e = threadIdx.x; e < ng * (C - 3); e += SH_THREADS) {
+                const int g = e / (C - 3), j = e - g * (C - 3);
+                tile[g * S + 3 + j] = __ldg(rs + e);
+            }
+    } else if (vec_ok && (C % 4 == 0)) {
         const float4 *src4 = reinterpret_cast<const float4 *>(src);
         for (int f = threadIdx.x; f < total / 4; f += SH_THREADS) {
             float4 v = ldg_stream4(src4 + f);
@@ -98,7 +110,11 @@ sh_forward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
     if (t >= ng) return;
     const int g = g0 + t;
     float Y[K];
-    sh_basis(nb, viewdirs[3 * g], viewdirs[3 * g + 1], viewdirs[3 * g + 2], Y);
+    {
+        float vx = viewdirs[3 * g], vy = viewdirs[3 * g + 1], vz = viewdirs[3 * g + 2];
+        if (cam_pos) { vx -= __ldg(cam_pos); vy -= __ldg(cam_pos + 1); vz -= __ldg(cam_pos + 2); }
+        sh_basis(nb, vx, vy, vz, Y);
+    }
     float row[S];
 #pragma unroll
     for (int j = 0; j < S; j += 4) {
@@ -128,7 +144,10 @@ template <int K>
 __global__ void __launch_bounds__(SH_THREADS)
 sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs,
                    const float *__restrict__ v_colors, float *__restrict__ v_coeffs, int vec_ok,
-                   const float *__restrict__ rgb_mask) {
+                   const float *__restrict__ rgb_mask,
+                   // split outputs (gsb_sh_backward_split): v_coeffs = v_features_dc [n,3], v_rest [n,K-1,3];
+                   // cam_pos != NULL: `viewdirs` holds the means
+                   int split, float *__restrict__ v_rest, const float *__restrict__ cam_pos) {
     constexpr int C = 3 * K;
     constexpr int S = sh_row_stride(K);
     __shared__ __align__(16) float tile[SH_THREADS * S];
@@ -139,7 +158,11 @@ sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs
     if (t < ng) {
         const int g = g0 + t;
         float Y[K];
-        sh_basis(nb, viewdirs[3 * g], viewdirs[3 * g + 1], viewdirs[3 * g + 2], Y);
+        {
+            float vx = viewdirs[3 * g], vy = viewdirs[3 * g + 1], vz = viewdirs[3 * g + 2];
+            if (cam_pos) { vx -= __ldg(cam_pos); vy -= __ldg(cam_pos + 1); vz -= __ldg(cam_pos + 2); }
+            sh_basis(nb, vx, vy, vz, Y);
+        }
         float v0 = v_colors[3 * g], v1 = v_colors[3 * g + 1], v2 = v_colors[3 * g + 2];
         if (rgb_mask) {  // gradient of clamp_min(colors + bias, 0): pass where the forward output was > 0
             v0 = (rgb_mask[3 * g] > 0.f) ? v0 : 0.f;
@@ -163,7 +186,15 @@ sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs
     __syncthreads();
     float *dst = v_coeffs + (size_t)g0 * C;
     const int total = ng * C;
-    if (vec_ok && (C % 4 == 0)) {
+    if (split) {
+        float *dc = v_coeffs + (size_t)g0 * 3, *rs = v_rest + (size_t)g0 * (C - 3);
+        for (int e = threadIdx.x; e < ng * 3; e += SH_THREADS) dc[e] = tile[(e / 3) * S + (e % 3)];
+        if (C > 3)
+            for (int e = threadIdx.x; e < ng * (C - 3); e += SH_THREADS) {
+                const int g = e / (C - 3), j = e - g * (C - 3);
+                rs[e] = tile[g * S + 3 + j];
+            }
+    } else if (vec_ok && (C % 4 == 0)) {
         float4 *dst4 = reinterpret_cast<float4 *>(dst);
         for (int f = threadIdx.x; f < total / 4; f += SH_THREADS) {
             int e = 4 * f, g = e / C, j = e - g * C;
@@ -346,14 +377,15 @@ int bases_of_degree(int degree) {
 }  // namespace
 
 static int launch_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *coeffs,
-                             float *colors, int fuse_rgb, float bias, gsb_stream_t stream) {
+                             float *colors, int fuse_rgb, float bias, gsb_stream_t stream, int split = 0,
+                             const float *rest = nullptr, const float *cam_pos = nullptr) {
     GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
     if (n == 0) return 0;
     GSB_CHECK_ARG(viewdirs && coeffs && colors);
     cudaStream_t s = (cudaStream_t)stream;
     int grid = gsb_div_up(n, SH_THREADS);
     int vec_ok = ((uintptr_t)coeffs % 16) == 0;
-#define GSB_SH_F(K) sh_forward_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok, fuse_rgb, bias)
+#define GSB_SH_F(K) sh_forward_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, coeffs, colors, vec_ok, fuse_rgb, bias, split, rest, cam_pos)
     switch (degree) {
         case 0: GSB_SH_F(1); break;
         case 1: GSB_SH_F(4); break;
@@ -367,14 +399,15 @@ static int launch_sh_forward(int n, int degree, int degrees_to_use, const float 
 }
 
 static int launch_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *v_colors,
-                              float *v_coeffs, const float *rgb_mask, gsb_stream_t stream) {
+                              float *v_coeffs, const float *rgb_mask, gsb_stream_t stream, int split = 0,
+                              float *v_rest = nullptr, const float *cam_pos = nullptr) {
     GSB_CHECK_ARG(n >= 0 && bases_of_degree(degree) > 0 && degrees_to_use >= 0 && degrees_to_use <= degree);
     if (n == 0) return 0;
     GSB_CHECK_ARG(viewdirs && v_colors && v_coeffs);
     cudaStream_t s = (cudaStream_t)stream;
     int grid = gsb_div_up(n, SH_THREADS);
     int vec_ok = ((uintptr_t)v_coeffs % 16) == 0;
-#define GSB_SH_B(K) sh_backward_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok, rgb_mask)
+#define GSB_SH_B(K) sh_backward_kernel<K><<<grid, SH_THREADS, 0, s>>>(n, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok, rgb_mask, split, v_rest, cam_pos)
     switch (degree) {
         case 0: GSB_SH_B(1); break;
         case 1: GSB_SH_B(4); break;
@@ -409,6 +442,27 @@ extern "C" int gsb_sh_backward_rgb(int n, int degree, int degrees_to_use, const 
                                    gsb_stream_t stream) {
     GSB_CHECK_ARG(n == 0 || rgbs);
     return launch_sh_backward(n, degree, degrees_to_use, viewdirs, v_rgbs, v_coeffs, rgbs, stream);
+}
+
+// Split variants (the rest of it): the colour pass of Model::forward without its ATen glue --
+//   viewdirs = means - cam_pos (detached; normalised inside like the reference kernel), coeffs =
+//   cat(featuresDc[:,None,:], featuresRest) (model.cpp:176-177,186-188: a 12K B/Gaussian copy forward and a split
+//   backward in autograd), rgbs = clamp_min(SH + bias, 0) (:192) -- reading the two feature tensors where they lie and
+//   writing their two gradients directly.
+extern "C" int gsb_sh_forward_split(int n, int degree, int degrees_to_use, const float *means, const float *cam_pos,
+                                    const float *features_dc, const float *features_rest, float bias, float *rgbs,
+                                    gsb_stream_t stream) {
+    GSB_CHECK_ARG(n == 0 || (cam_pos && features_dc && (degree == 0 || features_rest)));
+    return launch_sh_forward(n, degree, degrees_to_use, means, features_dc, rgbs, 1, bias, stream, 1, features_rest,
+                             cam_pos);
+}
+
+extern "C" int gsb_sh_backward_split(int n, int degree, int degrees_to_use, const float *means, const float *cam_pos,
+                                     const float *rgbs, const float *v_rgbs, float *v_features_dc,
+                                     float *v_features_rest, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n == 0 || (cam_pos && rgbs && v_features_dc && (degree == 0 || v_features_rest)));
+    return launch_sh_backward(n, degree, degrees_to_use, means, v_rgbs, v_features_dc, rgbs, stream, 1,
+                              v_features_rest, cam_pos);
 }
 
 // In-place gradient of clamp_min(. , 0): v_rgbs *= [rgbs > 0]  (what gsb_sh_backward_rgb does internally;

@@ -130,7 +130,6 @@ class GaussianModel:
         fov_x = 2.0 * math.atan(width / (2.0 * fx))
         fov_y = 2.0 * math.atan(height / (2.0 * fy))
         proj = projection_matrix(0.001, 1000.0, fov_x, fov_y, dev)
-        colors = torch.cat([self.featuresDc[:, None, :], self.featuresRest], 1)
         cam_pos = T.reshape(3).to(dev)
         scales, quats, opac, viewdirs = ops.ActivateGaussians.apply(self.means, self.scales, self.quats,
                                                                     self.opacities, cam_pos)
@@ -142,8 +141,10 @@ class GaussianModel:
         if float(radii.sum()) == 0.0:
             return self.backgroundColor.repeat(height, width, 1)
         degrees_to_use = min(step // self.shDegreeInterval, self.shDegree)
-        rgbs = ops.SphericalHarmonics.apply(degrees_to_use, viewdirs, colors)
-        rgbs = torch.clamp_min(rgbs + 0.5, 0.0)
+        # model.cpp:176-177,186-192 in one pass: no cat of featuresDc / featuresRest, view directions formed inside,
+        # + 0.5 and clamp_min fused (and their gradients written straight into the two feature tensors' grads)
+        rgbs = ops.SphericalHarmonicsRgb.apply(degrees_to_use, self.means.detach(), cam_pos, self.featuresDc,
+                                               self.featuresRest)
         rgb = ops.RasterizeGaussians.apply(xys, depths, radii, conics, num_tiles_hit, rgbs, opac, height, width,
                                            self.backgroundColor)
         return torch.clamp_max(rgb, 1.0)

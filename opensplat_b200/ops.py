@@ -422,6 +422,40 @@ class SphericalHarmonics(torch.autograd.Function):
         return None, None, compute_sh_backward(degree, degreesToUse, viewDirs, v_colors.contiguous())
 
 
+class SphericalHarmonicsRgb(torch.autograd.Function):
+    """The colour pass of Model::forward without its ATen glue (model.cpp:176-177,186-192):
+    rgbs = clamp_min(SH(degreesToUse, means - camPos, cat(featuresDc[:,None,:], featuresRest)) + 0.5, 0), reading the
+    two feature tensors where they lie and writing their two gradients directly (gsb_sh_forward_split /
+    gsb_sh_backward_split).  C++ twin: gsb::SphericalHarmonicsRgb (csrc/ops/fused_extras.hpp)."""
+
+    @staticmethod
+    def forward(ctx, degreesToUse, means, camPos, featuresDc, featuresRest):
+        n = means.shape[0]
+        degree = deg_from_sh(featuresRest.shape[-2] + 1)
+        if featuresDc.shape != (n, 3) or featuresRest.dim() != 3 or featuresRest.shape[2] != 3:
+            raise ValueError("featuresDc [N,3], featuresRest [N,K-1,3]")
+        m, dc, rest = capi.f32(means), capi.f32(featuresDc), capi.f32(featuresRest)
+        cp = capi.f32(torch.as_tensor(camPos, device=means.device)).reshape(3)
+        rgbs = _empty((n, 3), torch.float32, m)
+        capi.check(capi.lib().gsb_sh_forward_split(n, degree, int(degreesToUse), capi.ptr(m), capi.ptr(cp), capi.ptr(dc),
+                                                   capi.ptr(rest), 0.5, capi.ptr(rgbs), capi.stream()))
+        ctx.meta = (int(degreesToUse), degree, featuresRest.shape[-2])
+        ctx.save_for_backward(m, cp, rgbs)
+        return rgbs
+
+    @staticmethod
+    def backward(ctx, v_rgbs):
+        use, degree, kr = ctx.meta
+        m, cp, rgbs = ctx.saved_tensors
+        n = m.shape[0]
+        v_dc = _empty((n, 3), torch.float32, m)
+        v_rest = _empty((n, kr, 3), torch.float32, m)
+        capi.check(capi.lib().gsb_sh_backward_split(n, degree, use, capi.ptr(m), capi.ptr(cp), capi.ptr(rgbs),
+                                                    capi.ptr(capi.f32(v_rgbs)), capi.ptr(v_dc), capi.ptr(v_rest),
+                                                    capi.stream()))
+        return None, None, None, v_dc, v_rest
+
+
 class MainLoss(torch.autograd.Function):
     """Model::mainLoss (model.cpp:780-784): (1 - w) * L1 + w * (1 - SSIM), fused forward + gradient
     (gsb_ssim_l1_loss).  rendered, gt: [H,W,3] CUDA tensors.  Returns the scalar loss."""

@@ -173,3 +173,36 @@ def test_cpp_densify_stats_matches_python_path():
         dn.accumulate(v_xy, radii, H, W)
         o.densify_stats_(v_xy, radii, H, W, i == 0, gn, vc, ms)
     assert torch.equal(gn, dn.xys_grad_norm) and torch.equal(vc, dn.vis_counts) and torch.equal(ms, dn.max_2d_size)
+
+
+def test_cpp_fused_activation_and_colour_operators_match_python_mirrors():
+    """gsb::ActivateGaussians / gsb::SphericalHarmonicsRgb (csrc/ops/fused_extras.hpp: the opt-in one-liners for
+    model.cpp:148-150,176-177,186-192,200) against the Python autograd mirrors over the same C ABI -- forward and
+    gradients bit-identical (same kernels), and against the unfused op sequence to rounding."""
+    co = cpp_ops.ops()
+    torch.manual_seed(3)
+    n, K = 4099, 16
+    means = torch.randn(n, 3, device=DEV)
+    cam = torch.tensor([0.2, 0.1, -7.5])                      # host tensor: the operator moves it
+    ls, rq, ol = (torch.randn(n, k, device=DEV).requires_grad_() for k in (3, 4, 1))
+    dc = torch.randn(n, 3, device=DEV).requires_grad_()
+    rest = (0.3 * torch.randn(n, K - 1, 3, device=DEV)).requires_grad_()
+    w = [torch.randn(n, k, device=DEV) for k in (3, 4, 1, 3)]
+
+    def run(act, shrgb):
+        for t in (ls, rq, ol, dc, rest):
+            t.grad = None
+        s, q, o, vd = act(means, ls, rq, ol, cam)
+        rgbs = shrgb(2, means, cam, dc, rest)
+        ((s * w[0]).sum() + (q * w[1]).sum() + (o * w[2]).sum() + (rgbs * w[3]).sum()).backward()
+        return [t.detach().clone() for t in (s, q, o, vd, rgbs)] + [t.grad.clone() for t in (ls, rq, ol, dc, rest)]
+
+    a = run(co.activate_gaussians, co.spherical_harmonics_rgb)
+    b = run(ops.ActivateGaussians.apply, ops.SphericalHarmonicsRgb.apply)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    # unfused reference sequence
+    vd = (means - cam.to(DEV)) / (means - cam.to(DEV)).norm(dim=-1, keepdim=True)
+    ref = torch.clamp_min(co.spherical_harmonics(2, vd, torch.cat([dc[:, None, :], rest], 1).detach()) + 0.5, 0.0)
+    assert float((a[4] - ref).abs().max()) <= 3e-6
+    assert float((a[0] - torch.exp(ls.detach())).abs().max()) <= 2e-6 * float(torch.exp(ls.detach()).max())

@@ -71,6 +71,37 @@ def test_sh_fused_rgb_variants():
     assert float((rgbs == 0).float().mean()) > 0.05   # the clamp is active on this data
 
 
+@pytest.mark.parametrize("n,deg,use", [(1000, 3, 3), (129, 3, 1), (5003, 2, 2), (64, 0, 0), (300, 4, 4)])
+def test_sh_split_variant_matches_cat_sh_clamp(n, deg, use):
+    """gsb_sh_forward_split / _backward_split (featuresDc + featuresRest read where they lie, view direction formed in
+    the kernel, + 0.5 and clamp fused) against the reference's op sequence cat -> SphericalHarmonics -> clamp_min
+    (model.cpp:176-177,186-192) through autograd."""
+    rng = np.random.default_rng(n + deg)
+    K = (deg + 1) ** 2
+    means = cu(rng.uniform(-1, 1, (n, 3)).astype(np.float32))
+    cam = cu(np.array([0.3, -0.2, -8.0], np.float32))
+    dc = cu(rng.standard_normal((n, 3)).astype(np.float32)).requires_grad_()
+    rest = cu((0.3 * rng.standard_normal((n, K - 1, 3))).astype(np.float32)).requires_grad_()
+    w = cu(rng.standard_normal((n, 3)).astype(np.float32))
+    vd = means - cam
+    vd = vd / vd.norm(dim=-1, keepdim=True)
+    ref = torch.clamp_min(ops.SphericalHarmonics.apply(use, vd, torch.cat([dc[:, None, :], rest], 1)) + 0.5, 0.0)
+    (ref * w).sum().backward()
+    g_dc, g_rest = dc.grad.clone(), rest.grad.clone()
+    dc.grad = rest.grad = None
+    got = ops.SphericalHarmonicsRgb.apply(use, means, cam, dc, rest)
+    (got * w).sum().backward()
+    assert float((got - ref).abs().max()) <= 3e-6
+    assert float((got == 0).float().mean()) > 0.02 or deg == 0      # the clamp is active
+    # a clamp decision may flip where SH + 0.5 is within rounding of 0; everywhere else the gradients agree
+    same = ((got > 0) == (ref > 0)).all(dim=-1)
+    assert float(same.float().mean()) > 0.999
+    assert float((dc.grad - g_dc)[same].abs().max()) <= 3e-6
+    if K > 1:
+        assert float((rest.grad - g_rest)[same].abs().max()) <= 3e-6
+        assert float(rest.grad[:, (use + 1) ** 2 - 1:, :].abs().sum()) == 0.0     # bases above degreesToUse get 0
+
+
 # ------------------------------------------------------------------------------- projection + bins
 def _scene(n, W, H, scale, opacity=(0.05, 0.35), seed=0, **kw):
     return make_scene(n, W, H, scale=scale, sh_degree=0, opacity=opacity, seed=seed, **kw)

@@ -1,0 +1,21 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv > gpurun_out/r2_gpu.txt
+timeout 1800 python -m pytest tests -m gpu -x -q --timeout 900 > gpurun_out/r2_pytest1.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest1.log
+tail -5 gpurun_out/r2_pytest1.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench1.log 2> gpurun_out/r2_bench1.err; echo "bench rc=$?"
+tail -c 400 gpurun_out/r2_bench1.err
+# launch list of one step (shares)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 28 -c 28 --csv --log-file gpurun_out/r2_launches1.csv python tools/profile_step.py c2_1M_1080p_sh3 3 > gpurun_out/r2_launches1.out 2>&1
+# full capture of the binning + blend kernels, C2 and C5 (second step of two)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|tile_sort_pack|bin_count|bucket_emit|tile_scan|reduce_grad" -s 8 -c 8 -o gpurun_out/r2_prof_c2 python tools/profile_step.py c2_1M_1080p_sh3 2 > gpurun_out/r2_prof_c2.out 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|tile_sort_pack|bin_count|bucket_emit|reduce_grad" -s 7 -c 7 -o gpurun_out/r2_prof_c5 python tools/profile_step.py c5_5M_1440p_dense 2 > gpurun_out/r2_prof_c5.out 2>&1
+ls -la gpurun_out | tail -12
+# A/B: bitonic -> CTA radix switch point of the per-tile sort
+for v in 256 512 1024 2048; do
+  for wl in c2_1M_1080p_sh3 c5_5M_1440p_dense; do
+    GSB_LIB=opensplat_b200/lib/variants/lib_bitonic$v.so timeout 300 python tools/bench_blend.py $wl 10 >> gpurun_out/r2_ab_bitonic.log 2>&1
+  done
+done
+for wl in c2_1M_1080p_sh3 c5_5M_1440p_dense; do timeout 300 python tools/bench_blend.py $wl 10 >> gpurun_out/r2_ab_bitonic.log 2>&1; done
+cat gpurun_out/r2_ab_bitonic.log
