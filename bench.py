@@ -418,26 +418,47 @@ def run_ours(args):
         state["i"] = i + 1
         torch.cuda.current_stream().wait_event(cur["ev"])       # this step's H2D has landed
         tgt, vm, pm = cur["tgt"], cur["vm"], cur["pm"]
-        if world > 1:
+        if world > 1 and fused:
+            # gradients of the geometry tensors accumulate in place into the symmetric flat buffer the fused exchange
+            # all-reduces; the colour gradient lands in the symmetric v_rgb buffer the peers pull from
+            pipe.grad_flat[:pipe.geom_numel].zero_()
+            pipe.exchange.v_rgb.zero_()
+            for k in ("means", "scales", "quats", "opacities"):
+                P[k].grad = pipe.g[k]
+            P["coeffs"].grad = None
+        elif world > 1:
             gflat.zero_()
             for k in names:
                 P[k].grad = gviews[k]
         else:
             for t in P.values():
                 t.grad = None
-        if use_cpp:   # the libtorch autograd operators a C++ caller of the reference API uses
+        if world > 1 and fused:
+            # SH colours through the operator (forward); their backward + the cross-GPU reduction happen in the fused
+            # exchange launch, which expands every view's colour gradient into the coefficient gradient
+            with torch.no_grad():
+                rgbs = torch.clamp_min((cops.spherical_harmonics(3, pipe.viewdirs, P["coeffs"]) if use_cpp else
+                                        ops.compute_sh_forward(3, 3, pipe.viewdirs, P["coeffs"])) + 0.5, 0.0)
+            rgbs.requires_grad_()
+            rgbs.grad = pipe.exchange.v_rgb
+        elif use_cpp:   # the libtorch autograd operators a C++ caller of the reference API uses
             rgbs = torch.clamp_min(cops.spherical_harmonics(3, pipe.viewdirs, P["coeffs"]) + 0.5, 0.0)
+        else:
+            rgbs = torch.clamp_min(ops.SphericalHarmonics.apply(3, pipe.viewdirs, P["coeffs"]) + 0.5, 0.0)
+        if use_cpp:
             xys, depths, radii, conics, nth, _ = cops.project_gaussians(
                 P["means"], P["scales"], 1.0, P["quats"], vm, pm, fx, fy, cx, cy, H, W, 0.01)
             img = cops.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, P["opacities"], H, W, bg)
         else:
-            rgbs = torch.clamp_min(ops.SphericalHarmonics.apply(3, pipe.viewdirs, P["coeffs"]) + 0.5, 0.0)
             xys, depths, radii, conics, nth, _ = ops.ProjectGaussians.apply(
                 P["means"], P["scales"], 1.0, P["quats"], vm, pm, fx, fy, cx, cy, H, W, pipe.tb)
             img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, rgbs, P["opacities"], H, W, bg)
         loss = torch.nn.functional.mse_loss(img, tgt)
         loss.backward()
-        if world > 1:
+        if world > 1 and fused:
+            pipe.rgbs = rgbs.detach()                            # the clamp mask of the exchange
+            pipe.exchange.exchange(average=False)               # ONE fused launch: SH bwd of all views + all-reduce
+        elif world > 1:
             dist.all_reduce(gflat, op=dist.ReduceOp.SUM)        # ONE flat all-reduce of all per-Gaussian gradients
         cur["used"].record(torch.cuda.current_stream())
         cur["loss"].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H: the step's result
@@ -497,7 +518,8 @@ def run_ours(args):
                 "api": ("C++ libtorch autograd operators ProjectGaussians/RasterizeGaussians/SphericalHarmonics "
                         "(libopensplat_b200_ops.so via torch.ops)") if use_cpp else
                        "opensplat_b200.ops python autograd operators",
-                "exchange": "one NCCL all-reduce of the flat gradient buffer" if world > 1 else None},
+                "exchange": (("the fused exchange launch (as the device-timed arm)" if fused else
+                              "one NCCL all-reduce of the flat gradient buffer") if world > 1 else None)},
         "gpu_launches": launches_per_step(world, fused) * args.steps,
         "clocks": clocks,
         "roofline": roof, "roofline_path": roof_path,

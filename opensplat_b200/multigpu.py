@@ -52,10 +52,13 @@ class ViewParallelExchange:
         self.buf, self.hdl = t, hdl
         pipe.rebind_grad_flat(t[:pipe.numel])
         self.v_rgb = t[rgb_off:rgb_off + 3 * n].view(n, 3)
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        base_off = int(getattr(hdl, "offset", 0) or 0)      # the tensor's offset inside its symmetric allocation block
+        ptrs = [int(p) + base_off for p in hdl.buffer_ptrs]
         self.geom_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)              # peers' flat buffers
         self.rgb_ptrs = torch.tensor([p + 4 * rgb_off for p in ptrs], dtype=torch.int64, device=dev)
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if self.use_multicast else 0
+        mc = mc + base_off if mc else 0
+        assert ptrs[self.rank] == t.data_ptr(), "symmetric-memory handle does not describe this tensor"
         self.multicast_ptr = mc                                                           # 0: no NVSwitch multicast
         self.geom_numel = pipe.geom_numel   # means, scales, quats, opacities (16-byte aligned slices)
         assert self.geom_numel % 4 == 0

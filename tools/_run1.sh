@@ -19,3 +19,4 @@ for v in 256 512 1024 2048; do
 done
 for wl in c2_1M_1080p_sh3 c5_5M_1440p_dense; do timeout 300 python tools/bench_blend.py $wl 10 >> gpurun_out/r2_ab_bitonic.log 2>&1; done
 cat gpurun_out/r2_ab_bitonic.log
+timeout 900 python tools/bench_model_train.py --steps 20 > gpurun_out/r2_model_train.json 2> gpurun_out/r2_model_train.err; tail -c 600 gpurun_out/r2_model_train.json
