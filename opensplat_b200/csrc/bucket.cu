@@ -250,6 +250,16 @@ bucket_emit_kernel(int n, const GsbRecord *__restrict__ gattr, const float *__re
 
 typedef unsigned long long u64;
 
+// distribution sort of a tile's composites (tile_sort_pack_kernel)
+constexpr int DS_MIN_BINS = 64, DS_MAX_BINS = 2048;
+#ifndef GSB_DS_BIN_LIMIT
+#define GSB_DS_BIN_LIMIT 32     // a bin above this many entries (clustered depths) sends the tile to the comparison sorts
+#endif
+constexpr int DS_BIN_LIMIT = GSB_DS_BIN_LIMIT;
+#ifndef GSB_DSORT
+#define GSB_DSORT 1
+#endif
+
 #ifndef GSB_BITONIC_MAX
 #define GSB_BITONIC_MAX 4096   // lists up to this (padded) length use the bitonic network (measured faster), longer ones the radix sort
 #endif
@@ -362,6 +372,132 @@ __device__ __forceinline__ void cta_radix_sort_depth(u64 *buf, unsigned (*whist)
     }
 }
 
+// Gather + pack of one tile: record i of the tile = attributes of the Gaussian behind the i-th sorted composite.
+__device__ __forceinline__ void write_tile_records(const u64 *__restrict__ sorted, int L, int first,
+                                                   const int *__restrict__ gaussian_ids,
+                                                   const GsbRecord *__restrict__ gattr,
+                                                   GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
+                                                   int *__restrict__ gaussian_ids_sorted) {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const int k = (int)(unsigned)(sorted[i] & 0xffffffffull);
+        const int g = gaussian_ids[k];
+        const float4 *src = reinterpret_cast<const float4 *>(gattr + g);   // 3 x 128-bit gather (L2-resident)
+        float4 q0 = __ldg(src);
+        const float4 q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+        q0.w = __int_as_float(k);
+        float4 *dst = reinterpret_cast<float4 *>(records + first + i);
+        stg_stream4(dst, q0);
+        stg_stream4(dst + 1, q1);
+        stg_stream4(dst + 2, q2);
+        if (sorted_index) sorted_index[first + i] = k;
+        if (gaussian_ids_sorted) gaussian_ids_sorted[first + i] = g;
+    }
+}
+
+// K4a: distribution sort + pack.  Depths inside a tile are spread over [dmin, dmax]: bin the composites linearly in
+// depth into ~L/2 bins (the bin index is monotone in the depth bits), scatter them, let ONE thread order each (tiny)
+// bin by the full composite (depth bits, k) and pack.  Work is linear in L instead of the L log^2 L of a bitonic
+// network -- at C5's ~1000-entry lists an order of magnitude fewer instructions.  The result is the same total order
+// as any comparison sort of the composites.  A tile whose depths cluster (some bin above DS_BIN_LIMIT entries, or all
+// depths equal) is left to K4b (tile_done[tile] = 0), which also handles lists longer than this kernel's capacity.
+__global__ void __launch_bounds__(256)
+tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
+                       const int *__restrict__ gaussian_ids, const GsbRecord *__restrict__ gattr,
+                       GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
+                       int *__restrict__ gaussian_ids_sorted, const int *__restrict__ stats,
+                       unsigned char *__restrict__ tile_done) {
+    extern __shared__ unsigned long long dkey[];   // [cap] staged composites, [cap] scatter target
+    __shared__ int dhist[DS_MAX_BINS];             // bin sizes, then write cursors, finally bin ends
+    __shared__ int ds_scan[256 / 32 + 1];
+    __shared__ unsigned ds_lo, ds_hi;
+    __shared__ int ds_maxbin;
+    if (stats[2]) return;      // capacities exceeded: the host redoes the frame
+    const int tile = blockIdx.x;
+    const int2 range = tile_bins[tile];
+    const int L = range.y - range.x;
+    const int lane = threadIdx.x & 31;
+    if (L <= 0) { if (threadIdx.x == 0) tile_done[tile] = 1; return; }
+    if (L > cap) { if (threadIdx.x == 0) tile_done[tile] = 0; return; }
+    u64 *in = dkey, *out = dkey + cap;
+    if (L <= 64) {   // tiny lists: one warp, bitonic network in registers / shuffles
+        if (threadIdx.x < 32) {
+            u64 a = (lane < L) ? comp[range.x + lane] : ~0ull;
+            u64 b = (32 + lane < L) ? comp[range.x + 32 + lane] : ~0ull;
+#pragma unroll
+            for (int k = 2; k <= 64; k <<= 1) block64_substages(a, b, 0, lane, k, k >> 1);
+            out[lane] = a;
+            out[32 + lane] = b;
+        }
+        __syncthreads();
+        write_tile_records(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
+        if (threadIdx.x == 0) tile_done[tile] = 1;
+        return;
+    }
+    if (threadIdx.x == 0) { ds_lo = ~0u; ds_hi = 0u; ds_maxbin = 0; }
+    int nb = DS_MIN_BINS;
+    while (nb < (L >> 1) && nb < DS_MAX_BINS) nb <<= 1;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) dhist[b] = 0;
+    __syncthreads();
+    unsigned lo = ~0u, hi = 0u;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const u64 c = comp[range.x + i];
+        in[i] = c;
+        const unsigned d = (unsigned)(c >> 32);
+        lo = min(lo, d); hi = max(hi, d);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { atomicMin(&ds_lo, lo); atomicMax(&ds_hi, hi); }
+    __syncthreads();
+    if (ds_hi == ds_lo) { if (threadIdx.x == 0) tile_done[tile] = 0; return; }   // (uniform) one depth only
+    const float fmin = __uint_as_float(ds_lo);
+    const float scale = (float)nb / (__uint_as_float(ds_hi) - fmin);
+    auto bin_of = [&](u64 c) {
+        const int b = (int)((__uint_as_float((unsigned)(c >> 32)) - fmin) * scale);
+        return min(max(b, 0), nb - 1);
+    };
+    for (int i = threadIdx.x; i < L; i += blockDim.x) atomicAdd(&dhist[bin_of(in[i])], 1);
+    __syncthreads();
+    {   // exclusive scan over the nb bins (8 consecutive bins per thread) + the largest bin
+        int v[DS_MAX_BINS / 256], tsum = 0, tmax = 0;
+#pragma unroll
+        for (int q = 0; q < DS_MAX_BINS / 256; ++q) {
+            const int b = threadIdx.x * (DS_MAX_BINS / 256) + q;
+            v[q] = (b < nb) ? dhist[b] : 0;
+            tsum += v[q]; tmax = max(tmax, v[q]);
+        }
+        int total;
+        int run = block_excl_scan_i<256>(tsum, &total, ds_scan);
+        tmax = __reduce_max_sync(0xffffffffu, tmax);
+        if (lane == 0) atomicMax(&ds_maxbin, tmax);
+#pragma unroll
+        for (int q = 0; q < DS_MAX_BINS / 256; ++q) {
+            const int b = threadIdx.x * (DS_MAX_BINS / 256) + q;
+            if (b < nb) dhist[b] = run;     // write cursor of bin b; ends as the bin's end
+            run += v[q];
+        }
+    }
+    __syncthreads();
+    if (ds_maxbin > DS_BIN_LIMIT) { if (threadIdx.x == 0) tile_done[tile] = 0; return; }   // (uniform) clustered depths
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const u64 c = in[i];
+        out[atomicAdd(&dhist[bin_of(c)], 1)] = c;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        const int e = dhist[b], st = b ? dhist[b - 1] : 0;
+        for (int p = st + 1; p < e; ++p) {   // insertion sort by (depth bits, k)
+            const u64 c = out[p];
+            int q = p - 1;
+            while (q >= st && out[q] > c) { out[q + 1] = out[q]; --q; }
+            out[q + 1] = c;
+        }
+    }
+    __syncthreads();
+    write_tile_records(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
+    if (threadIdx.x == 0) tile_done[tile] = 1;
+}
+
 // One CTA per tile: sort the tile's composites (depth bits << 32 | k) ascending and write its records.
 //  * L <= 64: one warp, bitonic network in registers / shuffles;
 //  * longer:  CTA-wide LSD radix sort on the depth bits + tie fix-up (cta_radix_sort_depth).
@@ -370,13 +506,15 @@ __global__ void __launch_bounds__(256)
 tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
                       const int *__restrict__ gaussian_ids, const GsbRecord *__restrict__ gattr,
                       GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
-                      int *__restrict__ gaussian_ids_sorted, const int *__restrict__ stats) {
+                      int *__restrict__ gaussian_ids_sorted, const int *__restrict__ stats,
+                      const unsigned char *__restrict__ tile_done) {
     extern __shared__ unsigned long long skey[];
     __shared__ unsigned whist[8][256];
     __shared__ unsigned bin_base[256 + 8];
     __shared__ unsigned s_flag;
     if (stats[2]) return;      // capacities exceeded: the host redoes the frame
     const int tile = blockIdx.x;
+    if (tile_done && tile_done[tile]) return;   // already ordered and packed by tile_dsort_pack_kernel
     const int2 range = tile_bins[tile];
     const int L = range.y - range.x;
     if (L <= 0) return;
@@ -456,24 +594,11 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        const int k = (int)(unsigned)(skey[i] & 0xffffffffull);
-        const int g = gaussian_ids[k];
-        const float4 *src = reinterpret_cast<const float4 *>(gattr + g);   // 3 x 128-bit gather (L2-resident)
-        float4 q0 = __ldg(src);
-        const float4 q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-        q0.w = __int_as_float(k);
-        float4 *dst = reinterpret_cast<float4 *>(records + range.x + i);
-        stg_stream4(dst, q0);
-        stg_stream4(dst + 1, q1);
-        stg_stream4(dst + 2, q2);
-        if (sorted_index) sorted_index[range.x + i] = k;
-        if (gaussian_ids_sorted) gaussian_ids_sorted[range.x + i] = g;
-    }
+    write_tile_records(skey, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
 }
 
 struct BucketLayout {
-    size_t hdr, state_n, state_t, cursor, zero_bytes, gattr, comp, gids, total;
+    size_t hdr, state_n, state_t, cursor, zero_bytes, gattr, comp, gids, done, total;
     int nblk_n, nblk_t;
 };
 BucketLayout bucket_layout(int n, int m, int T) {
@@ -489,6 +614,7 @@ BucketLayout bucket_layout(int n, int m, int T) {
     L.gattr = o; o += gsb_align_up((size_t)n * sizeof(GsbRecord), 256);
     L.comp = o; o += gsb_align_up((size_t)m * 8, 256);
     L.gids = o; o += gsb_align_up((size_t)m * 4, 256);
+    L.done = o; o += gsb_align_up((size_t)(T > 0 ? T : 1), 256);   // per tile: ordered + packed by K4a
     L.total = o;
     return L;
 }
@@ -573,6 +699,20 @@ extern "C" int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, con
     GsbRecord *gattr = (GsbRecord *)(ws + L.gattr);
     bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, gattr, depths, radii, cum_tiles_hit, cull, tiles_x,
                                                          tiles_y, (int *)(ws + L.cursor), comp, gids, stats);
+    // K4a (distribution sort) stages the list twice in shared memory; lists beyond its capacity, and tiles whose
+    // depths cluster, are left to K4b (comparison sorts)
+    unsigned char *tile_done = nullptr;
+    if (GSB_DSORT) {
+        const int dcap = cap < 8192 ? cap : 8192;
+        const size_t dsmem = (size_t)dcap * 16;
+        tile_done = (unsigned char *)(ws + L.done);
+        if (dsmem > 32 * 1024)
+            GSB_CUDA(cudaFuncSetAttribute(tile_dsort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)dsmem));
+        tile_dsort_pack_kernel<<<T, 256, dsmem, s>>>(dcap, reinterpret_cast<const int2 *>(tile_bins), comp, gids,
+                                                    gattr, reinterpret_cast<GsbRecord *>(records), sorted_index,
+                                                    gaussian_ids_sorted, stats, tile_done);
+    }
     const size_t smem = (size_t)cap * 8;
 #define GSB_TSP(MAXI)                                                                                           \
     do {                                                                                                        \
@@ -581,7 +721,7 @@ extern "C" int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, con
                                           (int)smem));                                                          \
         tile_sort_pack_kernel<MAXI><<<T, 256, smem, s>>>(                                                       \
             cap, reinterpret_cast<const int2 *>(tile_bins), comp, gids, gattr,                                  \
-            reinterpret_cast<GsbRecord *>(records), sorted_index, gaussian_ids_sorted, stats);                  \
+            reinterpret_cast<GsbRecord *>(records), sorted_index, gaussian_ids_sorted, stats, tile_done);       \
     } while (0)
     if (cap <= 1024) GSB_TSP(4);
     else if (cap <= 4096) GSB_TSP(16);

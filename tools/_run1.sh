@@ -11,12 +11,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 28 -c 2
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|tile_sort_pack|bin_count|bucket_emit|tile_scan|reduce_grad" -s 8 -c 8 -o gpurun_out/r2_prof_c2 python tools/profile_step.py c2_1M_1080p_sh3 2 > gpurun_out/r2_prof_c2.out 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|tile_sort_pack|bin_count|bucket_emit|reduce_grad" -s 7 -c 7 -o gpurun_out/r2_prof_c5 python tools/profile_step.py c5_5M_1440p_dense 2 > gpurun_out/r2_prof_c5.out 2>&1
 ls -la gpurun_out | tail -12
-# A/B: bitonic -> CTA radix switch point of the per-tile sort
-for v in 256 512 1024 2048; do
+# A/B: per-tile sort: distribution sort (default) vs bitonic only vs CTA radix above 512
+for lib in default opensplat_b200/lib/variants/lib_nodsort.so opensplat_b200/lib/variants/lib_nodsort_radix512.so; do
   for wl in c2_1M_1080p_sh3 c5_5M_1440p_dense; do
-    GSB_LIB=opensplat_b200/lib/variants/lib_bitonic$v.so timeout 300 python tools/bench_blend.py $wl 10 >> gpurun_out/r2_ab_bitonic.log 2>&1
+    if [ "$lib" = default ]; then timeout 300 python tools/bench_blend.py $wl 10 >> gpurun_out/r2_ab_sort.log 2>&1
+    else GSB_LIB=$lib timeout 300 python tools/bench_blend.py $wl 10 >> gpurun_out/r2_ab_sort.log 2>&1; fi
   done
 done
-for wl in c2_1M_1080p_sh3 c5_5M_1440p_dense; do timeout 300 python tools/bench_blend.py $wl 10 >> gpurun_out/r2_ab_bitonic.log 2>&1; done
-cat gpurun_out/r2_ab_bitonic.log
+cat gpurun_out/r2_ab_sort.log
 timeout 900 python tools/bench_model_train.py --steps 20 > gpurun_out/r2_model_train.json 2> gpurun_out/r2_model_train.err; tail -c 600 gpurun_out/r2_model_train.json
