@@ -20,3 +20,4 @@ for lib in default opensplat_b200/lib/variants/lib_nodsort.so opensplat_b200/lib
 done
 cat gpurun_out/r2_ab_sort.log
 timeout 900 python tools/bench_model_train.py --steps 20 > gpurun_out/r2_model_train.json 2> gpurun_out/r2_model_train.err; tail -c 600 gpurun_out/r2_model_train.json
+timeout 120 opensplat_b200/lib/ubench_fp32 > gpurun_out/r2_ubench_fp32.txt 2>&1; cat gpurun_out/r2_ubench_fp32.txt
