@@ -603,6 +603,45 @@ def test_very_long_tile_lists_take_radix_and_generic_paths(n, expect_path):
     assert rel_l2(npy(colt.grad), r["v_colors"]) <= 1e-3 and rel_l2(npy(opt.grad), r["v_opacity"]) <= 1e-3
 
 
+def test_long_tile_lists_at_realistic_tile_counts():
+    """Tile lists between 4096 and 16384 entries on EVERY one of 256 tiles (not one pile-up tile): the distribution
+    sort with its largest shared-memory footprint, and -- with depth ties forced on half of the Gaussians -- the
+    comparison-sort fallback (CTA radix above 4096) at a realistic tile count.  Fast path (no cull) == generic path bit
+    for bit; operator image / gradients vs the oracle."""
+    n, W, H = 500_000, 256, 256
+    sc = _scene(n, W, H, 0.25, opacity=(0.002, 0.02), seed=4242)
+    left = sc["means"][:, 0] < 0          # left half of the image: heavy depth ties -> clustered bins -> fallback sorts;
+    sc["means"][left, 2] = np.round(sc["means"][left, 2] * 4) / 4   # right half: distinct depths -> distribution sort
+    rng = np.random.default_rng(3)
+    colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    cum = ops.cumsum_tiles_hit(nth)
+    tb = ops.tile_bounds(W, H)
+    colt, opt = cu(colors), cu(sc["opacities"])
+    m, max_len, bins_b, cum_b, stats, rec_b, idx_b, gs_b = _bucket_exact(xys, depths, radii, conics, colt, opt, tb,
+                                                                        cull=False)
+    lens = npy(bins_b)[:, 1] - npy(bins_b)[:, 0]
+    assert 4096 < max_len <= 16384 and (lens > 4096).mean() > 0.5, (max_len, float((lens > 4096).mean()))
+    isect, gids, ks, gs, bins, idx = ops.binAndSortGaussians(n, m, xys, depths, radii, cum, tb, return_index=True)
+    assert torch.equal(bins_b, bins) and torch.equal(idx_b, idx) and torch.equal(gs_b, gs)
+    bg = cu(np.array([0.1, 0.2, 0.3], np.float32))
+    out, fT, fI, rec = ops.rasterize_forward(tb, (W, H, 1), gs, idx, bins, xys, conics, colt, opt, bg)
+    assert torch.equal(rec_b[: m * 48], rec[: m * 48])
+    del isect, gids, ks, idx, rec_b, idx_b, gs_b
+    cg, og = colt.clone().requires_grad_(), opt.clone().requires_grad_()
+    img = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, cg, og, H, W, bg)
+    assert torch.equal(img, out)
+    o = orc.rasterize_forward(H, W, npy(gs), npy(bins), npy(xys), npy(conics), colors, sc["opacities"], [0.1, 0.2, 0.3],
+                              exp_mode=1)
+    ok, st = image_close(npy(img), o["out_img"], tol=2e-5, frac=2e-3)
+    assert ok, st
+    wgt = rng.uniform(-1, 1, (H, W, 3)).astype(np.float32)
+    (img * cu(wgt)).sum().backward()
+    r = orc.rasterize_backward(H, W, npy(gs), npy(bins), npy(xys), npy(conics), colors, sc["opacities"], [0.1, 0.2, 0.3],
+                               o["final_Ts"], o["final_idx"], wgt, exp_mode=1)
+    assert rel_l2(npy(cg.grad), r["v_colors"]) <= 1e-3 and rel_l2(npy(og.grad), r["v_opacity"]) <= 1e-3
+
+
 def test_dense_overlap_parity_c5_like():
     """Config C5 in miniature: ~200 candidate splats per pixel, saturating tiles, long lists (bitonic 2048-4096)."""
     n, W, H = 100_000, 320, 192
