@@ -108,7 +108,7 @@ def _python_simple_trainer(width, height, n, iters, lr=0.01):
 
 
 def test_reference_simple_trainer_unchanged_runs_on_b200_backend():
-    exe = os.path.join(ROOT, "opensplat_b200", "lib", "simple_trainer_b200")
+    exe = os.path.join(ROOT, "tests", "native", "_build", "simple_trainer_b200")
     if not os.path.exists(exe):
         pytest.skip("simple_trainer_b200 not built (needs /root/reference at build time)")
     iters, n, W, H = 30, 2000, 256, 256

@@ -20,7 +20,7 @@ from util import PARAM_NAMES  # noqa: E402
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "opensplat_b200", "lib", "libopensplat_model_b200.so")
+LIB = os.path.join(ROOT, "tests", "native", "_build", "libopensplat_model_b200.so")
 
 
 def make_problem(n=4000, V=3, H=96, W=128, k=4, seed=5):

@@ -53,7 +53,7 @@ def main():
     from opensplat_b200.densify import RefineConfig
     from opensplat_b200.model import Camera, GaussianModel, PARAM_NAMES
     cpp_ops.ops()
-    torch.ops.load_library(os.path.join(ROOT, "opensplat_b200", "lib", "libopensplat_model_b200.so"))
+    torch.ops.load_library(os.path.join(ROOT, "tests", "native", "_build", "libopensplat_model_b200.so"))
     W, H = a.W, a.H
     p, c2w, (fx, fy, cx, cy) = model_scene(a.n, W, H)
     gts = torch.rand(1, H, W, 3)

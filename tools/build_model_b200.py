@@ -1,5 +1,5 @@
 """Compiles the reference's model.cpp UNCHANGED (with -DUSE_CUDA) against the gsplat_b200 operator layer ->
-opensplat_b200/lib/libopensplat_model_b200.so, together with the test driver tests/native/model_driver.cpp
+tests/native/_build/libopensplat_model_b200.so (test artefact: the reference's code, not product), together with the test driver tests/native/model_driver.cpp
 (torch.ops.opensplat_b200_model.{train, after_train, save}).
 
 This is the drop-in check for the real caller of the hot path (model.cpp:147-218 must compile
@@ -23,7 +23,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-OUT = os.path.join(ROOT, "opensplat_b200", "lib", "libopensplat_model_b200.so")
+OUT = os.path.join(ROOT, "tests", "native", "_build", "libopensplat_model_b200.so")
 
 
 def build(force=False):
@@ -36,6 +36,7 @@ def build(force=False):
     deps = [driver, build_ops.OUT, os.path.join(REF, "model.cpp"), os.path.join(REF, "model.hpp"), __file__]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
     tmp = "/tmp/gsb_model_b200"
     os.makedirs(tmp, exist_ok=True)
     for f in ("model.cpp", "model.hpp"):
@@ -61,7 +62,7 @@ def build(force=False):
         objs = list(ex.map(cc, srcs))
     lib = os.path.join(ROOT, "opensplat_b200", "lib")
     cmd = [cxx, "-shared", "-o", OUT] + objs + build_ops.shared_stdcxx_flags() + [
-        f"-L{lib}", "-lopensplat_b200_ops", "-lgsplat_b200", "-Wl,-rpath,$ORIGIN", f"-L{T}/lib",
+        f"-L{lib}", "-lopensplat_b200_ops", "-lgsplat_b200", "-Wl,-rpath,$ORIGIN/../../../opensplat_b200/lib", f"-L{T}/lib",
         f"-Wl,-rpath,{T}/lib", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
         "-L/usr/local/cuda/lib64", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,5 +1,5 @@
 """Compiles the reference's simple_trainer.cpp UNCHANGED against the gsplat_b200 operator layer
-(opensplat_b200/csrc/ops headers + libopensplat_b200_ops.so) -> opensplat_b200/lib/simple_trainer_b200.
+(opensplat_b200/csrc/ops headers + libopensplat_b200_ops.so) -> tests/native/_build/simple_trainer_b200 (test artefact: the reference's code, not product).
 
 Only possible where /root/reference exists (the build container); the binary travels to the GPU box.
 The source file is compiled from a scratch copy under /tmp so that its quoted #includes resolve to THIS
@@ -16,7 +16,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/simple_trainer.cpp"
-OUT = os.path.join(ROOT, "opensplat_b200", "lib", "simple_trainer_b200")
+OUT = os.path.join(ROOT, "tests", "native", "_build", "simple_trainer_b200")
 
 
 def build():
@@ -26,6 +26,7 @@ def build():
     from opensplat_b200 import build_ops
     build_ops.build()
     shared_stdcxx_flags = build_ops.shared_stdcxx_flags
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
     tmp = "/tmp/gsb_simple_trainer"
     os.makedirs(tmp, exist_ok=True)
     shutil.copy(REF, os.path.join(tmp, "simple_trainer.cpp"))
@@ -36,7 +37,7 @@ def build():
     cmd = ["g++", "-std=c++17", "-O2", "-DUSE_CUDA", "-D_GLIBCXX_USE_CXX11_ABI=1", "-w",
            f"-I{ops}", f"-I{shims}", f"-I{T}/include", f"-I{T}/include/torch/csrc/api/include",
            "-I/usr/local/cuda/include", os.path.join(tmp, "simple_trainer.cpp"), os.path.join(shims, "cv_utils.cpp"),
-           "-o", OUT] + shared_stdcxx_flags() + [f"-L{lib}", "-lopensplat_b200_ops", "-lgsplat_b200", "-Wl,-rpath,$ORIGIN",
+           "-o", OUT] + shared_stdcxx_flags() + [f"-L{lib}", "-lopensplat_b200_ops", "-lgsplat_b200", "-Wl,-rpath,$ORIGIN/../../../opensplat_b200/lib",
            f"-L{T}/lib", f"-Wl,-rpath,{T}/lib", "-Wl,--no-as-needed", "-ltorch", "-ltorch_cpu", "-ltorch_cuda",
            "-lc10", "-lc10_cuda", "-L/usr/local/cuda/lib64", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
