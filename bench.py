@@ -258,8 +258,7 @@ def _side_config(workload, dev, steps=5, warmup=3):
     n, W, H, _, _ = WORKLOADS[workload]
     rec = {"value": W * H / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
            "gaussians": n, "width": W, "height": H, "intersections_binned": pipe.m,
-           "intersections_reference": int(pipe.nth.sum()), "longest_tile_list": pipe.max_len,
-           "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "roofline": roof, "roofline_path": roof_path}
+XX: {k: round(v, 4) for k, v in stage_ms.items()}, "roofline": roof, "roofline_path": roof_path}
     del pipe
     torch.cuda.empty_cache()
     return rec
@@ -352,6 +351,7 @@ def run_ours(args):
     value = world * W * H / (ms_step * 1e-3) / 1e6
     pairs = _pair_counts(pipe)
     m_ref = int(pipe.nth.sum())
+    occupancy = pipe.tile_occupancy()
 
     # per-rank work and compute time (separates view skew from the exchange): every rank's binned M, longest tile
     # list and the sum of its own stages without the exchange stage
@@ -525,6 +525,7 @@ def run_ours(args):
         "roofline": roof, "roofline_path": roof_path,
         "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
         "per_rank": per_rank,
+        "tile_occupancy": occupancy,
         "exchange_check": exchange_check,
         "other_configs": side or None,
         "cpu_baseline": cpu,

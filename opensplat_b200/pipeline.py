@@ -330,6 +330,20 @@ class SplatPipeline:
         if self.exchange is not None:
             self.exchange.resize(self)
 
+    def tile_occupancy(self, nbins=16):
+        """Diagnostic: histogram of the tile-list lengths of the last frame (binned lists).
+        Host-side, outside any timed region."""
+        tb = self.tile_bins.cpu().numpy()
+        lens = (tb[:, 1] - tb[:, 0]).astype("int64")
+        import numpy as np
+        mx = int(lens.max()) if lens.size else 0
+        edges = np.linspace(0, max(mx, 1), nbins + 1)
+        hist, _ = np.histogram(lens, bins=edges)
+        q = np.percentile(lens, [50, 90, 99]) if lens.size else [0, 0, 0]
+        return {"tiles": int(lens.size), "empty_tiles": int((lens == 0).sum()), "mean": float(lens.mean()),
+                "p50": float(q[0]), "p90": float(q[1]), "p99": float(q[2]), "max": mx,
+                "hist_edges": [round(float(e), 1) for e in edges], "hist": [int(h) for h in hist]}
+
     # algorithmic HBM bytes of the path for the last step (SURVEY.md 8d / BASELINE.md section 4)
     def algorithmic_bytes(self):
         n, m, P, T, K = self.n, self.m, self.W * self.H, self.T, self.K
