@@ -21,3 +21,7 @@ done
 cat gpurun_out/r2_ab_sort.log
 timeout 900 python tools/bench_model_train.py --steps 20 > gpurun_out/r2_model_train.json 2> gpurun_out/r2_model_train.err; tail -c 600 gpurun_out/r2_model_train.json
 timeout 120 opensplat_b200/lib/ubench_fp32 > gpurun_out/r2_ubench_fp32.txt 2>&1; cat gpurun_out/r2_ubench_fp32.txt
+# sanitizers on the new kernels (binning v2, distribution sort, exchange launch): smoke() + the exchange tests
+timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_san_memcheck_smoke.txt 2>&1; tail -3 gpurun_out/r2_san_memcheck_smoke.txt
+timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_exchange.py -x -q > gpurun_out/r2_san_memcheck_exchange.txt 2>&1; tail -3 gpurun_out/r2_san_memcheck_exchange.txt
+timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_san_racecheck_smoke.txt 2>&1; tail -3 gpurun_out/r2_san_racecheck_smoke.txt
