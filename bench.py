@@ -30,11 +30,11 @@ WORKLOADS = {
 
 
 # kernels of OURS launched per fwd+bwd step (counted from the C-ABI implementations, fast binning path):
-#   sh_fwd(+clamp) 1, project_fwd 1, bin_count_scan 1, tile_scan 1, bucket_emit 1, tile_dsort_pack 1,
+#   sh_fwd(+clamp) 1, project_fwd 1, bin_count 1, count_scan 1, tile_scan 1, bucket_emit 1, tile_dsort_pack 1,
 #   tile_sort_pack (fallback pass) 1, blend_fwd 1, mse 1, blend_bwd 1, row_reduce 1, project_bwd 1, sh_bwd 1
 #   (N>1 fused exchange: mask 1 + exchange 1 instead of sh_bwd; the two cross-rank barriers are torch's kernels)
 def launches_per_step(world=1, fused=True, train=False):
-    n = 12 + (2 if (world > 1 and fused) else 1)
+    n = 13 + (2 if (world > 1 and fused) else 1)
     return n + (1 if train else 0)
 
 
@@ -258,7 +258,9 @@ def _side_config(workload, dev, steps=5, warmup=3):
     n, W, H, _, _ = WORKLOADS[workload]
     rec = {"value": W * H / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
            "gaussians": n, "width": W, "height": H, "intersections_binned": pipe.m,
-XX: {k: round(v, 4) for k, v in stage_ms.items()}, "roofline": roof, "roofline_path": roof_path}
+           "intersections_reference": int(pipe.nth.sum()), "longest_tile_list": pipe.max_len,
+           "tile_occupancy": pipe.tile_occupancy(),
+           "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "roofline": roof, "roofline_path": roof_path}
     del pipe
     torch.cuda.empty_cache()
     return rec

@@ -5,9 +5,9 @@
 // (forward.cu:148-169).  The same ORDER -- by tile, then depth bits, ties by ascending unsorted slot k (what a
 // stable sort of the Gaussian-major emission gives) -- is produced here without a global sort and without a
 // host read-back in the middle:
-//   K1 bin_count_scan : per Gaussian, build its 48-B attribute record once, count the tiles it is binned to (one
-//                       atomic per tile -> tile sizes) and scan the per-Gaussian counts in the same kernel
-//                       (single-pass chained scan, decoupled look-back) -> cum_tiles_hit (the gradient-row slots)
+//   K1 bin_count      : per Gaussian, build its 48-B attribute record once and count the tiles it is binned to (one
+//                       atomic per tile -> tile sizes); K1b count_scan: single-pass chained scan (decoupled look-back)
+//                       of the per-Gaussian counts -> cum_tiles_hit (the gradient-row slots)
 //   K2 tile_scan      : exclusive scan over the T tiles (chained scan over <= 32 CTAs) -> tile_bins (first, last+1),
 //                       write cursors, stats = {M, longest list, overflow flag}
 //   K3 bucket_emit    : per Gaussian, write (depth bits << 32 | k) into its tiles' segments (atomic cursor;
@@ -131,50 +131,80 @@ __device__ __forceinline__ int chained_scan_prefix(unsigned long long *state, in
     return excl;
 }
 
-// K1: attribute record + tile counting + per-Gaussian scan
+// K1: attribute record + tile counting; writes the per-Gaussian count of binned tiles (scanned by K1b)
 __global__ void __launch_bounds__(BIN_THREADS)
-bin_count_scan_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii,
-                      const float *__restrict__ conics, const float *__restrict__ colors,
-                      const float *__restrict__ opacities, int cull, int tiles_x, int tiles_y, BinHeader *hdr,
-                      unsigned long long *state, int *__restrict__ tile_count, GsbRecord *__restrict__ gattr,
-                      int *__restrict__ cum_out) {
+bin_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii,
+                 const float *__restrict__ conics, const float *__restrict__ colors,
+                 const float *__restrict__ opacities, int cull, int tiles_x, int tiles_y,
+                 int *__restrict__ tile_count, GsbRecord *__restrict__ gattr, int *__restrict__ count_out) {
+    const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int cnt = 0;
+    const int r = radii[i];
+    if (r > 0) {
+        const float2 c = xys[i];
+        // the record of this Gaussian is built ONCE here (log2 / sqrt / extents) and only copied per intersection
+        const GsbRecord rec = make_record(c, __ldg(conics + 3 * i), __ldg(conics + 3 * i + 1),
+                                          __ldg(conics + 3 * i + 2), __ldg(opacities + i), __ldg(colors + 3 * i),
+                                          __ldg(colors + 3 * i + 1), __ldg(colors + 3 * i + 2), 0);
+        float4 *dst = reinterpret_cast<float4 *>(gattr + i);
+        dst[0] = rec.q0; dst[1] = rec.q1; dst[2] = rec.q2;
+        int x0, x1, y0, y1;
+        tile_bbox_of(c, r, tiles_x, tiles_y, x0, x1, y0, y1);
+        for (int ty = y0; ty < y1; ++ty)
+            for (int tx = x0; tx < x1; ++tx) {
+                if (cull && !extent_slot_mask(c.x, c.y, rec.q1.w, rec.q2.w, (float)(tx * GSB_TILE),
+                                              (float)(ty * GSB_TILE)))
+                    continue;
+                atomicAdd(&tile_count[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
+                ++cnt;
+            }
+    }
+    count_out[i] = cnt;
+}
+
+// K1b: in-place inclusive scan of the per-Gaussian counts -> cum_tiles_hit (the gradient-row slots).  Single pass:
+// 2048 counts per block, chained scan across blocks (decoupled look-back over ticket-ordered blocks).
+constexpr int GS_IPT = 8;
+__global__ void __launch_bounds__(BIN_THREADS)
+count_scan_kernel(int n, int *__restrict__ counts_then_cum, BinHeader *hdr, unsigned long long *state) {
     __shared__ int sm[BIN_THREADS / 32 + 1];
     __shared__ int s_blk, s_prefix;
     if (threadIdx.x == 0) s_blk = (int)atomicAdd(&hdr->ticket_n, 1u);
     __syncthreads();
     const int blk = s_blk;
-    const int i = blk * BIN_THREADS + threadIdx.x;
-    int cnt = 0;
-    if (i < n) {
-        const int r = radii[i];
-        if (r > 0) {
-            const float2 c = xys[i];
-            // the record of this Gaussian is built ONCE here (log2 / sqrt / extents) and only copied per intersection
-            const GsbRecord rec = make_record(c, __ldg(conics + 3 * i), __ldg(conics + 3 * i + 1),
-                                              __ldg(conics + 3 * i + 2), __ldg(opacities + i), __ldg(colors + 3 * i),
-                                              __ldg(colors + 3 * i + 1), __ldg(colors + 3 * i + 2), 0);
-            float4 *dst = reinterpret_cast<float4 *>(gattr + i);
-            dst[0] = rec.q0; dst[1] = rec.q1; dst[2] = rec.q2;
-            int x0, x1, y0, y1;
-            tile_bbox_of(c, r, tiles_x, tiles_y, x0, x1, y0, y1);
-            for (int ty = y0; ty < y1; ++ty)
-                for (int tx = x0; tx < x1; ++tx) {
-                    if (cull && !extent_slot_mask(c.x, c.y, rec.q1.w, rec.q2.w, (float)(tx * GSB_TILE),
-                                                  (float)(ty * GSB_TILE)))
-                        continue;
-                    atomicAdd(&tile_count[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
-                    ++cnt;
-                }
-        }
+    const int e0 = (blk * BIN_THREADS + threadIdx.x) * GS_IPT;
+    int v[GS_IPT];
+    const bool vec = (e0 + GS_IPT <= n) && ((reinterpret_cast<uintptr_t>(counts_then_cum + e0) & 15) == 0);
+    if (vec) {
+        const int4 a = *reinterpret_cast<const int4 *>(counts_then_cum + e0);
+        const int4 b = *reinterpret_cast<const int4 *>(counts_then_cum + e0 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < GS_IPT; ++k) v[k] = (e0 + k < n) ? counts_then_cum[e0 + k] : 0;
     }
+    int tsum = 0;
+#pragma unroll
+    for (int k = 0; k < GS_IPT; ++k) tsum += v[k];
     int total;
-    const int excl = block_excl_scan_i<BIN_THREADS>(cnt, &total, sm);
+    int run = block_excl_scan_i<BIN_THREADS>(tsum, &total, sm);
     if (threadIdx.x < 32) {
         const int p = chained_scan_prefix(state, blk, total);
         if (threadIdx.x == 0) s_prefix = p;
     }
     __syncthreads();
-    if (i < n) cum_out[i] = s_prefix + excl + cnt;
+    run += s_prefix;
+#pragma unroll
+    for (int k = 0; k < GS_IPT; ++k) { run += v[k]; v[k] = run; }
+    if (vec) {
+        *reinterpret_cast<int4 *>(counts_then_cum + e0) = make_int4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<int4 *>(counts_then_cum + e0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < GS_IPT; ++k)
+            if (e0 + k < n) counts_then_cum[e0 + k] = v[k];
+    }
 }
 
 // K2: exclusive scan of the tile sizes -> tile_bins, write cursors, stats = {M, longest list, overflow, 0}
@@ -603,7 +633,7 @@ struct BucketLayout {
 };
 BucketLayout bucket_layout(int n, int m, int T) {
     BucketLayout L;
-    L.nblk_n = gsb_div_up(n > 0 ? n : 1, BIN_THREADS);
+    L.nblk_n = gsb_div_up(n > 0 ? n : 1, BIN_THREADS * GS_IPT);   // blocks of the count scan (K1b)
     L.nblk_t = gsb_div_up(T > 0 ? T : 1, TSCAN_THREADS);
     size_t o = 0;
     L.hdr = o; o += sizeof(BinHeader);
@@ -658,9 +688,11 @@ extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *ra
     GSB_CUDA(cudaMemsetAsync(ws, 0, L.zero_bytes, s));
     if (n > 0) {
         GSB_CHECK_ARG(xys && radii && conics && colors && opacities && cum_tiles_hit && ((uintptr_t)xys % 8) == 0);
-        bin_count_scan_kernel<<<L.nblk_n, BIN_THREADS, 0, s>>>(
-            n, reinterpret_cast<const float2 *>(xys), radii, conics, colors, opacities, cull, tiles_x, tiles_y, hdr,
-            (unsigned long long *)(ws + L.state_n), cursor, (GsbRecord *)(ws + L.gattr), cum_tiles_hit);
+        bin_count_kernel<<<gsb_div_up(n, BIN_THREADS), BIN_THREADS, 0, s>>>(
+            n, reinterpret_cast<const float2 *>(xys), radii, conics, colors, opacities, cull, tiles_x, tiles_y, cursor,
+            (GsbRecord *)(ws + L.gattr), cum_tiles_hit);
+        count_scan_kernel<<<L.nblk_n, BIN_THREADS, 0, s>>>(n, cum_tiles_hit, hdr,
+                                                          (unsigned long long *)(ws + L.state_n));
     }
     tile_scan_kernel<<<L.nblk_t, TSCAN_THREADS, 0, s>>>(T, L.nblk_t, m_capacity, len_capacity, hdr,
                                                        (unsigned long long *)(ws + L.state_t), cursor,

@@ -435,7 +435,7 @@ class SphericalHarmonicsRgb(torch.autograd.Function):
         if featuresDc.shape != (n, 3) or featuresRest.dim() != 3 or featuresRest.shape[2] != 3:
             raise ValueError("featuresDc [N,3], featuresRest [N,K-1,3]")
         m, dc, rest = capi.f32(means), capi.f32(featuresDc), capi.f32(featuresRest)
-        cp = capi.f32(torch.as_tensor(camPos, device=means.device)).reshape(3)
+        cp = capi.f32(torch.as_tensor(camPos).to(means.device)).reshape(3)
         rgbs = _empty((n, 3), torch.float32, m)
         capi.check(capi.lib().gsb_sh_forward_split(n, degree, int(degreesToUse), capi.ptr(m), capi.ptr(cp), capi.ptr(dc),
                                                    capi.ptr(rest), 0.5, capi.ptr(rgbs), capi.stream()))
@@ -491,7 +491,8 @@ class ActivateGaussians(torch.autograd.Function):
     def forward(ctx, means, log_scales, raw_quats, opacity_logits, cam_pos):
         n = means.shape[0]
         means, ls, rq = capi.f32(means), capi.f32(log_scales), capi.f32(raw_quats)
-        ol, cp = capi.f32(opacity_logits).reshape(-1), capi.f32(cam_pos).reshape(3)
+        ol = capi.f32(opacity_logits).reshape(-1)
+        cp = capi.f32(torch.as_tensor(cam_pos).to(means.device)).reshape(3)   # a host tensor is accepted (as in C++)
         scales, quats = torch.empty_like(ls), torch.empty_like(rq)
         opac = torch.empty((n, 1), dtype=torch.float32, device=means.device)
         vd = torch.empty_like(means)

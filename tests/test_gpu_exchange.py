@@ -40,7 +40,8 @@ def test_multiview_sh_backward_matches_sum_of_single_view_vjps(num_views, n, deg
     ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
     out = torch.full((n, K, 3), 9.0, device=DEV)
     scale = 1.0 / num_views
-    capi.check(L.gsb_sh_backward_multiview(n, deg, use, capi.ptr(cu(means)), num_views, capi.ptr(cu(cams)),
+    means_d, cams_d = cu(means), cu(cams)      # keep the device copies alive across the (asynchronous) launch
+    capi.check(L.gsb_sh_backward_multiview(n, deg, use, capi.ptr(means_d), num_views, capi.ptr(cams_d),
                                            ptrs.data_ptr(), scale, capi.ptr(out), capi.stream()))
     # (a) sum of the single-view kernel (the path a single GPU runs), (b) the oracle in float64
     acc = torch.zeros((n, K, 3), device=DEV, dtype=torch.float64)
@@ -48,7 +49,8 @@ def test_multiview_sh_backward_matches_sum_of_single_view_vjps(num_views, n, deg
     one = torch.empty((n, K, 3), device=DEV)
     for r in range(num_views):
         vd = (means - cams[r]).astype(np.float32)
-        capi.check(L.gsb_sh_backward(n, deg, use, capi.ptr(cu(vd)), capi.ptr(bufs[r]), capi.ptr(one), capi.stream()))
+        vd_d = cu(vd)
+        capi.check(L.gsb_sh_backward(n, deg, use, capi.ptr(vd_d), capi.ptr(bufs[r]), capi.ptr(one), capi.stream()))
         acc += one.double()
         ref64 += orc.sh_backward(use, K, vd, v[r]).astype(np.float64)
     got = out.cpu().numpy().astype(np.float64)
@@ -91,9 +93,10 @@ def test_exchange_launch_does_both_roles_at_once():
     geom = torch.randn(4 * 5000, device=DEV)
     g0 = geom.clone()
     gp = torch.tensor([geom.data_ptr()], dtype=torch.int64, device=DEV)
-    capi.check(L.gsb_sh_backward_multiview(n, deg, deg, capi.ptr(cu(means)), views, capi.ptr(cu(cams)), ptrs.data_ptr(),
+    means_d, cams_d = cu(means), cu(cams)
+    capi.check(L.gsb_sh_backward_multiview(n, deg, deg, capi.ptr(means_d), views, capi.ptr(cams_d), ptrs.data_ptr(),
                                            0.5, capi.ptr(out_a), capi.stream()))
-    capi.check(L.gsb_exchange_gradients(n, deg, deg, capi.ptr(cu(means)), views, capi.ptr(cu(cams)), ptrs.data_ptr(),
+    capi.check(L.gsb_exchange_gradients(n, deg, deg, capi.ptr(means_d), views, capi.ptr(cams_d), ptrs.data_ptr(),
                                         0.5, capi.ptr(out_b), 0, 1, geom.numel(), gp.data_ptr(), None, capi.stream()))
     assert torch.equal(out_a, out_b) and torch.equal(geom, g0 * 0.5)
 

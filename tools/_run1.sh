@@ -6,10 +6,10 @@ tail -5 gpurun_out/r2_pytest1.log
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench1.log 2> gpurun_out/r2_bench1.err; echo "bench rc=$?"
 tail -c 400 gpurun_out/r2_bench1.err
 # launch list of one step (shares)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 13 -c 26 --csv --log-file gpurun_out/r2_launches1.csv python tools/profile_step.py c2_1M_1080p_sh3 3 > gpurun_out/r2_launches1.out 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 18 -c 28 --csv --log-file gpurun_out/r2_launches1.csv python tools/profile_step.py c2_1M_1080p_sh3 3 > gpurun_out/r2_launches1.out 2>&1
 # full capture of the binning + blend kernels, C2 and C5 (second step of two)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|sort_pack|bin_count|bucket_emit|tile_scan|reduce_grad" -s 8 -c 8 -o gpurun_out/r2_prof_c2 python tools/profile_step.py c2_1M_1080p_sh3 2 > gpurun_out/r2_prof_c2.out 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|sort_pack" -s 4 -c 4 -o gpurun_out/r2_prof_c5 python tools/profile_step.py c5_5M_1440p_dense 2 > gpurun_out/r2_prof_c5.out 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|sort_pack|bin_count|count_scan|bucket_emit|tile_scan|reduce_grad" -s 13 -c 9 -o gpurun_out/r2_prof_c2 python tools/profile_step.py c2_1M_1080p_sh3 2 > gpurun_out/r2_prof_c2.out 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rasterize_|sort_pack" -s 5 -c 4 -o gpurun_out/r2_prof_c5 python tools/profile_step.py c5_5M_1440p_dense 2 > gpurun_out/r2_prof_c5.out 2>&1
 ls -la gpurun_out | tail -12
 # A/B: per-tile sort: distribution sort (default) vs bitonic only vs CTA radix above 512
 for lib in default opensplat_b200/lib/variants/lib_nodsort.so opensplat_b200/lib/variants/lib_nodsort_radix512.so; do

@@ -11,7 +11,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 STAGE_OF = {"rasterize_backward_kernel": "raster_bwd", "rasterize_forward_kernel": "raster_fwd",
             "tile_dsort_pack_kernel": "tile_dsort_pack", "tile_sort_pack_kernel": "tile_sort_pack",
-            "bin_count_scan_kernel": "bin_count_scan", "bucket_emit_kernel": "bucket_emit",
+            "bin_count_kernel": "bin_count", "count_scan_kernel": "count_scan", "bucket_emit_kernel": "bucket_emit",
             "tile_scan_kernel": "tile_scan", "reduce_grad_rows_kernel": "reduce_grad_rows"}
 
 
