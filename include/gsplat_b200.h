@@ -176,21 +176,25 @@ int gsb_gather_bin_edges(int m, int num_tiles, const int64_t *isect_ids_sorted,
  * gsb_bucket_sort_pack: fills `records`; optional outputs sorted_index [M] / gaussian_ids_sorted [M] (NULL to
  *   skip).  Returns GSB_ERR_UNSUPPORTED if len_capacity > gsb_bucket_max_tile_len() -- take the generic path.
  * gsb_rasterize_forward_packed: the blend kernel alone on an already packed record stream; m = the m_capacity
- *   the records buffer was sized with; bin_stats may be NULL. */
+ *   the records buffer was sized with; bin_stats may be NULL.
+ * tile_order (optional everywhere, [tiles] int32): a permutation of the tile ids, longest list first, written by
+ *   gsb_bucket_tile_ranges and consumed by gsb_rasterize_forward_packed / gsb_rasterize_backward_ordered: the
+ *   persistent blend warps take tiles in that order, so the tiles still running when the kernel drains are the
+ *   cheapest ones.  No result depends on it (tiles are independent). */
 int gsb_bucket_max_tile_len(void);
 size_t gsb_bucket_workspace_bytes(int n, int m_capacity, int num_tiles);
 int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *radii, const float *conics, const float *colors,
                            const float *opacities, int cull, int tiles_x, int tiles_y, int m_capacity,
                            int len_capacity, void *workspace, size_t workspace_bytes, int32_t *cum_tiles_hit,
-                           int32_t *tile_bins, int32_t *stats, gsb_stream_t stream);
+                           int32_t *tile_bins, int32_t *tile_order, int32_t *stats, gsb_stream_t stream);
 int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, const float *depths, const int32_t *radii,
                          const int32_t *cum_tiles_hit, int cull, int tiles_x, int tiles_y, const int32_t *tile_bins,
                          const int32_t *stats, void *workspace, size_t workspace_bytes, void *records,
                          int32_t *sorted_index, int32_t *gaussian_ids_sorted, gsb_stream_t stream);
 int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, int tiles_y, int m,
-                                 const int32_t *tile_bins, const int32_t *bin_stats, const float *background,
-                                 void *records, float *out_img, float *final_Ts, int32_t *final_idx,
-                                 gsb_stream_t stream);
+                                 const int32_t *tile_bins, const int32_t *tile_order, const int32_t *bin_stats,
+                                 const float *background, void *records, float *out_img, float *final_Ts,
+                                 int32_t *final_idx, gsb_stream_t stream);
 
 /* ---- Rasterization ---------------------------------------------------------------------------
  * gsb_rasterize_forward replaces rasterize_forward_tensor (bindings.h:110-125, bindings.cu:338-410,
@@ -216,6 +220,12 @@ int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tiles_y, int m,
                           const float *colors, const float *opacities, const float *background,
                           void *records, float *out_img, float *final_Ts, int32_t *final_idx,
                           gsb_stream_t stream);
+int gsb_rasterize_backward_ordered(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
+                                   const int32_t *tile_bins, const int32_t *tile_order, const float *conics,
+                                   const float *opacities, void *records, const int32_t *cum_tiles_hit,
+                                   const float *background, const float *final_Ts, const int32_t *final_idx,
+                                   const float *v_output, const float *v_output_alpha, void *grad_rows, float *v_xy,
+                                   float *v_conic, float *v_colors, float *v_opacity, gsb_stream_t stream);
 /* gsb_rasterize_forward_count: diagnostic twin of gsb_rasterize_forward_packed (same outputs) that also ACCUMULATES
  *   into pair_counts (device uint64[4]; zero it first) {records that pass the per-record extent test, slot visits
  *   (x 32 lanes = pixel tests), pixel pairs evaluated (sigma inside the extent: one ex2), pixel pairs blended} --

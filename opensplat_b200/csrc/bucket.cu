@@ -35,15 +35,25 @@ constexpr int CUR_STRIDE = 32;  // ints
 constexpr int BIN_THREADS = 256;
 constexpr int TSCAN_THREADS = 1024;
 
-struct BinHeader {          // 256 B at the start of the workspace, zeroed by the call's memset
-    unsigned ticket_n;      // dynamic block ids of K1 (order of the chained scan)
+constexpr int LEN_BUCKETS = 64;
+struct BinHeader {          // 1 KB at the start of the workspace, zeroed by the call's memset
+    unsigned ticket_n;      // dynamic block ids of K1b (order of the chained scan)
     unsigned ticket_t;      // ... of K2
     unsigned done_t;        // K2 blocks finished
     int max_len;            // longest tile list (atomicMax)
     int total;              // M
-    int pad[59];
+    int pad0[3];
+    int len_hist[LEN_BUCKETS];   // tiles per list-length bucket (K2), for the longest-first tile order (K2b)
+    int len_cur[LEN_BUCKETS];    // K2b write cursors
+    int pad[120];
 };
-static_assert(sizeof(BinHeader) == 256, "header is 256 bytes");
+static_assert(sizeof(BinHeader) == 1024, "header is 1 KB");
+
+// list-length bucket of a tile: 64 linear buckets over [0, len_capacity]
+__device__ __forceinline__ int len_bucket(int v, int len_capacity) {
+    const long long b = (long long)v * LEN_BUCKETS / ((long long)max(len_capacity, 1) + 1);
+    return (int)(b < LEN_BUCKETS - 1 ? b : LEN_BUCKETS - 1);
+}
 
 __device__ __forceinline__ void tile_bbox_of(float2 c, int r, int tiles_x, int tiles_y, int &x0, int &x1, int &y0,
                                              int &y1) {
@@ -218,6 +228,7 @@ tile_scan_kernel(int T, int nblk, int m_capacity, int len_capacity, BinHeader *h
     const int blk = s_blk;
     const int t = blk * TSCAN_THREADS + threadIdx.x;
     const int v = (t < T) ? tile_count_then_cursor[(size_t)t * CUR_STRIDE] : 0;
+    if (t < T) atomicAdd(&hdr->len_hist[len_bucket(v, len_capacity)], 1);
     int total;
     const int excl = block_excl_scan_i<TSCAN_THREADS>(v, &total, sm);
     const int wmax = __reduce_max_sync(0xffffffffu, v);
@@ -247,6 +258,27 @@ tile_scan_kernel(int T, int nblk, int m_capacity, int len_capacity, BinHeader *h
             stats[3] = 0;
         }
     }
+}
+
+// K2b: tile order for the persistent blend kernels, longest list first.  A blend warp owns a tile for 1/2 .. 1/3 of
+// the whole kernel's duration, so the kernel ends with a tail in which the last-started tiles run on mostly empty SMs;
+// handing the tiles out longest-first makes those last ones the cheapest (measured / modelled: profiles/).
+// Order inside a length bucket is arbitrary (tiles are independent: no result depends on it).
+__global__ void __launch_bounds__(TSCAN_THREADS)
+tile_order_kernel(int T, int len_capacity, BinHeader *hdr, const int2 *__restrict__ tile_bins,
+                  int *__restrict__ tile_order) {
+    __shared__ int base[LEN_BUCKETS];
+    if (threadIdx.x < LEN_BUCKETS) {
+        int sfx = 0;
+        for (int b = LEN_BUCKETS - 1; b > (int)threadIdx.x; --b) sfx += hdr->len_hist[b];
+        base[threadIdx.x] = sfx;
+    }
+    __syncthreads();
+    const int t = blockIdx.x * TSCAN_THREADS + threadIdx.x;
+    if (t >= T) return;
+    const int2 r = tile_bins[t];
+    const int b = len_bucket(r.y - r.x, len_capacity);
+    tile_order[base[b] + atomicAdd(&hdr->len_cur[b], 1)] = t;
 }
 
 // K3: write the composites (depth bits << 32 | k) into the tiles' segments
@@ -672,7 +704,7 @@ extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *ra
                                       const float *colors, const float *opacities, int cull, int tiles_x,
                                       int tiles_y, int m_capacity, int len_capacity, void *workspace,
                                       size_t workspace_bytes, int32_t *cum_tiles_hit, int32_t *tile_bins,
-                                      int32_t *stats, gsb_stream_t stream) {
+                                      int32_t *tile_order, int32_t *stats, gsb_stream_t stream) {
     GSB_CHECK_ARG(n >= 0 && tiles_x > 0 && tiles_y > 0 && m_capacity >= 0 && len_capacity >= 0);
     GSB_CHECK_ARG(tile_bins && stats && workspace && ((uintptr_t)workspace % 256) == 0);
     const int T = tiles_x * tiles_y;
@@ -697,6 +729,9 @@ extern "C" int gsb_bucket_tile_ranges(int n, const float *xys, const int32_t *ra
     tile_scan_kernel<<<L.nblk_t, TSCAN_THREADS, 0, s>>>(T, L.nblk_t, m_capacity, len_capacity, hdr,
                                                        (unsigned long long *)(ws + L.state_t), cursor,
                                                        reinterpret_cast<int2 *>(tile_bins), stats);
+    if (tile_order)
+        tile_order_kernel<<<L.nblk_t, TSCAN_THREADS, 0, s>>>(T, len_capacity, hdr,
+                                                            reinterpret_cast<const int2 *>(tile_bins), tile_order);
     GSB_LAUNCH_CHECK();
     return 0;
 }

@@ -123,6 +123,8 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
 
     torch::Tensor cum = torch::empty({n}, gsb::like(x, torch::kInt32));
     torch::Tensor tileBins = torch::empty({numTiles, 2}, gsb::like(x, torch::kInt32));
+    torch::Tensor tileOrder = torch::empty({numTiles}, gsb::like(x, torch::kInt32));   // longest list first
+    bool ordered = true;
     torch::Tensor stats = torch::empty({4}, gsb::like(x, torch::kInt32));
     torch::Tensor outImg = torch::empty({imgHeight, imgWidth, 3}, gsb::like(x, torch::kFloat32));
     torch::Tensor finalTs = torch::empty({imgHeight, imgWidth}, gsb::like(x, torch::kFloat32));
@@ -142,7 +144,7 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
         gsb::check(gsb_bucket_tile_ranges(n, gsb::fp(x), r.data_ptr<int32_t>(), gsb::fp(con), gsb::fp(col),
                                           gsb::fp(op), cull, tilesX, tilesY, mCap, lenCap, wp, wsBytes,
                                           cum.data_ptr<int32_t>(), tileBins.data_ptr<int32_t>(),
-                                          stats.data_ptr<int32_t>(), gsb::stream()),
+                                          tileOrder.data_ptr<int32_t>(), stats.data_ptr<int32_t>(), gsb::stream()),
                    "gsb_bucket_tile_ranges");
         statsHost.copy_(stats, /*non_blocking=*/true);
         at::cuda::CUDAEvent statsReady;
@@ -154,7 +156,8 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
                                             records.data_ptr(), nullptr, nullptr, gsb::stream()),
                        "gsb_bucket_sort_pack");
         gsb::check(gsb_rasterize_forward_packed(imgHeight, imgWidth, tilesX, tilesY, mCap,
-                                                tileBins.data_ptr<int32_t>(), stats.data_ptr<int32_t>(), gsb::fp(bg),
+                                                tileBins.data_ptr<int32_t>(), tileOrder.data_ptr<int32_t>(),
+                                                stats.data_ptr<int32_t>(), gsb::fp(bg),
                                                 records.data_ptr(), gsb::fpw(outImg), gsb::fpw(finalTs),
                                                 finalIdx.data_ptr<int32_t>(), gsb::stream()),
                    "gsb_rasterize_forward_packed");
@@ -188,13 +191,15 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
                                          finalIdx.data_ptr<int32_t>(), gsb::stream()),
                    "gsb_rasterize_forward");
         mRaster = mRef;
+        ordered = false;
         break;
     }
 
     ctx->saved_data["imgWidth"] = imgWidth;
     ctx->saved_data["imgHeight"] = imgHeight;
     ctx->saved_data["numIntersects"] = mRaster;
-    ctx->save_for_backward({tileBins, con, op, records, cum, bg, finalTs, finalIdx});
+    ctx->saved_data["ordered"] = ordered;
+    ctx->save_for_backward({tileBins, con, op, records, cum, bg, finalTs, finalIdx, tileOrder});
     return outImg;
 }
 
@@ -204,7 +209,8 @@ tensor_list RasterizeGaussians::backward(AutogradContext *ctx, tensor_list grad_
     const int m = (int)ctx->saved_data["numIntersects"].toInt();
     variable_list saved = ctx->get_saved_variables();
     torch::Tensor tileBins = saved[0], con = saved[1], op = saved[2], records = saved[3], cum = saved[4];
-    torch::Tensor bg = saved[5], finalTs = saved[6], finalIdx = saved[7];
+    torch::Tensor bg = saved[5], finalTs = saved[6], finalIdx = saved[7], tileOrder = saved[8];
+    const bool ordered = ctx->saved_data["ordered"].toBool();
     const int n = (int)con.size(0);
     c10::cuda::CUDAGuard guard(con.device());
     torch::Tensor v_out = gsb::f32(grad_outputs[0]);  // may arrive as an expanded (stride-0) tensor
@@ -214,8 +220,9 @@ tensor_list RasterizeGaussians::backward(AutogradContext *ctx, tensor_list grad_
     torch::Tensor v_colors = torch::empty({n, 3}, gsb::like(con, torch::kFloat32));
     torch::Tensor v_opacity = torch::empty({n, 1}, gsb::like(con, torch::kFloat32));
     // v_output_alpha is identically zero in the reference (rasterize_gaussians.cpp:108) -> NULL
-    gsb::check(gsb_rasterize_backward(imgHeight, imgWidth, (imgWidth + BLOCK_X - 1) / BLOCK_X,
+    gsb::check(gsb_rasterize_backward_ordered(imgHeight, imgWidth, (imgWidth + BLOCK_X - 1) / BLOCK_X,
                                       (imgHeight + BLOCK_Y - 1) / BLOCK_Y, n, m, tileBins.data_ptr<int32_t>(),
+                                      ordered ? tileOrder.data_ptr<int32_t>() : nullptr,
                                       gsb::fp(con), gsb::fp(op), records.data_ptr(), cum.data_ptr<int32_t>(),
                                       gsb::fp(bg), gsb::fp(finalTs), finalIdx.data_ptr<int32_t>(), gsb::fp(v_out),
                                       nullptr, rows.data_ptr(), gsb::fpw(v_xy), gsb::fpw(v_conic),

@@ -51,7 +51,7 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                           const float *__restrict__ background, const float *__restrict__ final_Ts,
                           const int *__restrict__ final_idx, const float *__restrict__ v_output,
                           const float *__restrict__ v_output_alpha, float *__restrict__ grad_rows,
-                          unsigned *__restrict__ tile_counter) {
+                          unsigned *__restrict__ tile_counter, const int *__restrict__ tile_order) {
     __shared__ WarpRing rings[RK_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpRing &ring = rings[warp];
@@ -69,6 +69,7 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= num_tiles) break;
+        if (tile_order) tile = __ldg(tile_order + tile);   // tickets are handed out longest list first
         const int2 range = tile_bins[tile];
         if (range.y <= range.x) continue;
 
@@ -299,14 +300,14 @@ extern "C" size_t gsb_raster_grad_rows_bytes(int m) {
     return gsb_align_up((size_t)(m > 0 ? m : 0) * GSB_GRAD_ROW_FLOATS * 4 + 256, 256);
 }
 
-extern "C" int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
-                                      const int32_t *tile_bins, const float *conics,
-                                      const float *opacities, void *records,
-                                      const int32_t *cum_tiles_hit, const float *background,
-                                      const float *final_Ts, const int32_t *final_idx,
-                                      const float *v_output, const float *v_output_alpha,
-                                      void *grad_rows, float *v_xy, float *v_conic, float *v_colors,
-                                      float *v_opacity, gsb_stream_t stream) {
+static int rasterize_backward_impl(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
+                                   const int32_t *tile_bins, const int32_t *tile_order, const float *conics,
+                                   const float *opacities, void *records,
+                                   const int32_t *cum_tiles_hit, const float *background,
+                                   const float *final_Ts, const int32_t *final_idx,
+                                   const float *v_output, const float *v_output_alpha,
+                                   void *grad_rows, float *v_xy, float *v_conic, float *v_colors,
+                                   float *v_opacity, gsb_stream_t stream) {
     GSB_CHECK_ARG(img_h > 0 && img_w > 0 && n >= 0 && m >= 0);
     GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
     if (n == 0) return 0;
@@ -324,11 +325,38 @@ extern "C" int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int til
         rasterize_backward_kernel<<<grid, RK_THREADS, 0, s>>>(
             img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
             reinterpret_cast<const GsbRecord *>(records), background, final_Ts, final_idx, v_output,
-            v_output_alpha, reinterpret_cast<float *>(grad_rows), counters);
+            v_output_alpha, reinterpret_cast<float *>(grad_rows), counters, tile_order);
     }
     reduce_grad_rows_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(
         n, cum_tiles_hit, reinterpret_cast<const float *>(grad_rows), conics, opacities,
         reinterpret_cast<float2 *>(v_xy), v_conic, v_colors, v_opacity);
     GSB_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
+                                      const int32_t *tile_bins, const float *conics,
+                                      const float *opacities, void *records,
+                                      const int32_t *cum_tiles_hit, const float *background,
+                                      const float *final_Ts, const int32_t *final_idx,
+                                      const float *v_output, const float *v_output_alpha,
+                                      void *grad_rows, float *v_xy, float *v_conic, float *v_colors,
+                                      float *v_opacity, gsb_stream_t stream) {
+    return rasterize_backward_impl(img_h, img_w, tiles_x, tiles_y, n, m, tile_bins, nullptr, conics, opacities, records,
+                                   cum_tiles_hit, background, final_Ts, final_idx, v_output, v_output_alpha, grad_rows,
+                                   v_xy, v_conic, v_colors, v_opacity, stream);
+}
+
+// Same, with the tile order of gsb_bucket_tile_ranges (tiles handed to the persistent warps longest list first).
+extern "C" int gsb_rasterize_backward_ordered(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
+                                              const int32_t *tile_bins, const int32_t *tile_order,
+                                              const float *conics, const float *opacities, void *records,
+                                              const int32_t *cum_tiles_hit, const float *background,
+                                              const float *final_Ts, const int32_t *final_idx,
+                                              const float *v_output, const float *v_output_alpha,
+                                              void *grad_rows, float *v_xy, float *v_conic, float *v_colors,
+                                              float *v_opacity, gsb_stream_t stream) {
+    return rasterize_backward_impl(img_h, img_w, tiles_x, tiles_y, n, m, tile_bins, tile_order, conics, opacities,
+                                   records, cum_tiles_hit, background, final_Ts, final_idx, v_output, v_output_alpha,
+                                   grad_rows, v_xy, v_conic, v_colors, v_opacity, stream);
 }

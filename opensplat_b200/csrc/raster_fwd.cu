@@ -62,7 +62,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                          const float *__restrict__ background, float *__restrict__ out_img,
                          float *__restrict__ final_Ts, int *__restrict__ final_idx,
                          unsigned *__restrict__ tile_counter, const int *__restrict__ bin_stats,
-                         unsigned long long *__restrict__ pair_counts) {
+                         unsigned long long *__restrict__ pair_counts, const int *__restrict__ tile_order) {
     // bin_stats (optional): stats of gsb_bucket_tile_ranges; [2] != 0 means the binning overflowed its
     // capacities and wrote nothing -- the host redoes the frame, this launch must not touch the records
     if (bin_stats && bin_stats[2]) return;
@@ -84,6 +84,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
         if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= num_tiles) break;
+        if (tile_order) tile = __ldg(tile_order + tile);   // tickets are handed out longest list first
 
         const int tx = tile % tiles_x, ty = tile / tiles_x;
         const int X = tx * GSB_TILE + (lane & 15);
@@ -276,14 +277,15 @@ extern "C" int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tile
     rasterize_forward_kernel<false><<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
         reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr,
-        nullptr);
+        nullptr, nullptr);
     GSB_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, int tiles_y, int m,
-                                            const int32_t *tile_bins, const int32_t *bin_stats,
-                                            const float *background, void *records, float *out_img,
+                                            const int32_t *tile_bins, const int32_t *tile_order,
+                                            const int32_t *bin_stats, const float *background, void *records,
+                                            float *out_img,
                                             float *final_Ts, int32_t *final_idx, gsb_stream_t stream) {
     GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0);
     GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
@@ -298,7 +300,7 @@ extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, i
     rasterize_forward_kernel<false><<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
         reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, bin_stats,
-        nullptr);
+        nullptr, tile_order);
     GSB_LAUNCH_CHECK();
     return 0;
 }
@@ -323,7 +325,7 @@ extern "C" int gsb_rasterize_forward_count(int img_h, int img_w, int tiles_x, in
     rasterize_forward_kernel<true><<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
         reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr,
-        pair_counts);
+        pair_counts, nullptr);
     GSB_LAUNCH_CHECK();
     return 0;
 }

@@ -243,14 +243,18 @@ def bucket_tile_ranges(xys, radii, conics, colors, opacities, tile_bounds_, m_ca
         workspace = torch.empty(L.gsb_bucket_workspace_bytes(n, m_capacity, T) + 256, dtype=torch.uint8,
                                 device=xys.device)
     off = (-workspace.data_ptr()) % 256
-    bins = _empty((T, 2), torch.int32, xys)
+    # tile_bins [T,2] followed by the longest-first tile order [T] in ONE tensor (rows 0..T-1 / the flat tail), so that
+    # whoever holds the bins also holds the order the blend kernels should take the tiles in
+    binord = _empty((3 * T,), torch.int32, xys)
+    bins, order = binord[:2 * T].view(T, 2), binord[2 * T:]
     cum = _empty((n,), torch.int32, xys)
     stats = _empty((4,), torch.int32, xys)
     capi.check(L.gsb_bucket_tile_ranges(
         n, capi.ptr(capi.f32(xys)), capi.ptr(radii.contiguous()), capi.ptr(capi.f32(conics)),
         capi.ptr(capi.f32(colors)), capi.ptr(capi.f32(opacities)), 1 if cull else 0, tile_bounds_[0],
         tile_bounds_[1], m_capacity, len_capacity, workspace.data_ptr() + off, workspace.numel() - off,
-        capi.ptr(cum), capi.ptr(bins), capi.ptr(stats), capi.stream()))
+        capi.ptr(cum), capi.ptr(bins), capi.ptr(order), capi.ptr(stats), capi.stream()))
+    bins.tile_order = order
     return bins, cum, stats, workspace
 
 
@@ -271,13 +275,16 @@ def bucket_sort_pack(n, m_capacity, len_capacity, depths, radii, cum_tiles_hit, 
     return records, idx, gs
 
 
-def rasterize_forward_packed(tile_bounds_, img_size, m_capacity, tile_bins, records, background, stats=None):
+def rasterize_forward_packed(tile_bounds_, img_size, m_capacity, tile_bins, records, background, stats=None,
+                             tile_order=None):
     W, H = img_size[0], img_size[1]
     out = _empty((H, W, 3), torch.float32, records)
     fT = _empty((H, W), torch.float32, records)
     fI = _empty((H, W), torch.int32, records)
+    if tile_order is None:
+        tile_order = getattr(tile_bins, "tile_order", None)
     capi.check(capi.lib().gsb_rasterize_forward_packed(
-        H, W, tile_bounds_[0], tile_bounds_[1], m_capacity, capi.ptr(tile_bins), capi.ptr(stats),
+        H, W, tile_bounds_[0], tile_bounds_[1], m_capacity, capi.ptr(tile_bins), capi.ptr(tile_order), capi.ptr(stats),
         capi.ptr(capi.f32(background)), capi.ptr(records), capi.ptr(out), capi.ptr(fT), capi.ptr(fI),
         capi.stream()))
     return out, fT, fI
@@ -303,7 +310,7 @@ def rasterize_forward(tile_bounds_, img_size, gaussian_ids_sorted, sorted_index,
 
 
 def rasterize_backward(img_height, img_width, n, m, tile_bins, conics, opacities, records, cum_tiles_hit,
-                       background, final_Ts, final_idx, v_output, v_output_alpha=None):
+                       background, final_Ts, final_idx, v_output, v_output_alpha=None, tile_order=None):
     L = capi.lib()
     tb = tile_bounds(img_width, img_height)
     rows = _ws.get(final_Ts.device, "grad_rows", L.gsb_raster_grad_rows_bytes(m) + 16)
@@ -313,8 +320,8 @@ def rasterize_backward(img_height, img_width, n, m, tile_bins, conics, opacities
     v_colors = _empty((n, 3), torch.float32, final_Ts)
     v_opacity = _empty((n, 1), torch.float32, final_Ts)
     v_output = capi.f32(v_output)
-    capi.check(L.gsb_rasterize_backward(
-        img_height, img_width, tb[0], tb[1], n, m, capi.ptr(tile_bins), capi.ptr(capi.f32(conics)),
+    capi.check(L.gsb_rasterize_backward_ordered(
+        img_height, img_width, tb[0], tb[1], n, m, capi.ptr(tile_bins), capi.ptr(tile_order), capi.ptr(capi.f32(conics)),
         capi.ptr(capi.f32(opacities)), capi.ptr(records), capi.ptr(cum_tiles_hit),
         capi.ptr(capi.f32(background)), capi.ptr(final_Ts), capi.ptr(final_idx),
         capi.ptr(v_output), capi.ptr(v_output_alpha) if v_output_alpha is not None else None,
@@ -393,16 +400,19 @@ class RasterizeGaussians(torch.autograd.Function):
                                                      colors, opacity, background)
             break
         ctx.meta = (int(imgHeight), int(imgWidth), numPoints, m_cap)
-        ctx.save_for_backward(bins, conics, opacity, records, cum, background, fT, fI)
+        order = getattr(bins, "tile_order", None)
+        ctx.has_order = order is not None
+        ctx.save_for_backward(bins, conics, opacity, records, cum, background, fT, fI,
+                              order if order is not None else bins)
         return out
 
     @staticmethod
     def backward(ctx, v_outImg):
         H, W, n, m = ctx.meta
-        bins, conics, opacity, records, cum, background, fT, fI = ctx.saved_tensors
+        bins, conics, opacity, records, cum, background, fT, fI, order = ctx.saved_tensors
         v_xy, v_conic, v_colors, v_opacity = rasterize_backward(H, W, n, m, bins, conics, opacity, records, cum,
-                                                                background, fT, fI,
-                                                                v_outImg.contiguous(), None)
+                                                                background, fT, fI, v_outImg.contiguous(), None,
+                                                                tile_order=order if ctx.has_order else None)
         # 10 slots; grads for xys(0), conics(3), colors(5), opacity(6) (rasterize_gaussians.cpp:129-139)
         return v_xy, None, None, v_conic, None, v_colors, v_opacity, None, None, None
 

@@ -40,6 +40,8 @@ class SplatPipeline:
         self.background = torch.zeros(3, dtype=f32, device=d)
         self.loss = torch.zeros(1, dtype=f32, device=d)
         self.tile_bins = torch.empty((self.T, 2), dtype=i32, device=d)
+        self.tile_order = torch.empty((self.T,), dtype=i32, device=d)   # longest-first tile order (fast path)
+        self.use_tile_order = os.environ.get("GSB_TILE_ORDER", "1") != "0"
         self.stats_dev = torch.zeros(4, dtype=i32, device=d)
         self.plan = BinPlan()   # capacities of the M-dependent buffers, carried from frame to frame
         self.cull = True        # bin only (Gaussian, tile) pairs whose extent box touches the tile
@@ -202,7 +204,9 @@ class SplatPipeline:
                 self._stage("scan")
                 capi.check(L.gsb_bucket_tile_ranges(n, P(self.xys), P(self.radii), P(self.conics), P(self.rgbs),
                                                     P(p["opacities"]), cull, self.tb[0], self.tb[1], m_cap, len_cap,
-                                                    wsp, wsb, P(self.cum), P(self.tile_bins), P(self.stats_dev), s))
+                                                    wsp, wsb, P(self.cum), P(self.tile_bins),
+                                                    P(self.tile_order) if self.use_tile_order else None,
+                                                    P(self.stats_dev), s))
                 plan.read_back(self.stats_dev)
                 if m_cap > 0:
                     self._stage("bucket_sort_pack")
@@ -211,12 +215,14 @@ class SplatPipeline:
                                                       P(self.stats_dev), wsp, wsb, P(self.records), None, None, s))
                 self._stage("raster_fwd")
                 capi.check(L.gsb_rasterize_forward_packed(H, W, self.tb[0], self.tb[1], m_cap, P(self.tile_bins),
+                                                          P(self.tile_order) if self.use_tile_order else None,
                                                           P(self.stats_dev), P(self.background), P(self.records),
                                                           P(self.out_img), P(self.final_Ts), P(self.final_idx), s))
                 self._stage("end_fwd")
                 self.m, self.max_len, overflow = plan.wait()
                 if not overflow:
                     self.m_raster = m_cap
+                    self._ordered = self.use_tile_order
                     return self.out_img
                 self._ev = []            # the frame is redone: drop its stage events
                 if self.max_len > limit:
@@ -249,6 +255,7 @@ class SplatPipeline:
                                            P(self.rgbs), P(p["opacities"]), P(self.background), P(self.records),
                                            P(self.out_img), P(self.final_Ts), P(self.final_idx), s))
         self.m_raster = m
+        self._ordered = False
         self._stage("end_fwd")
         return self.out_img
 
@@ -263,7 +270,8 @@ class SplatPipeline:
         capi.check(L.gsb_mse_loss_grad(cnt, P(self.out_img), P(self.target), P(self.v_img), P(self.loss), 1.0 / cnt, s))
         v_rgbs = self.exchange.v_rgbs_buffer() if self.exchange is not None else self.v_rgbs
         self._stage("raster_bwd")
-        capi.check(L.gsb_rasterize_backward(H, W, self.tb[0], self.tb[1], n, m, P(self.tile_bins), P(self.conics),
+        capi.check(L.gsb_rasterize_backward_ordered(H, W, self.tb[0], self.tb[1], n, m, P(self.tile_bins),
+                                            P(self.tile_order) if self._ordered else None, P(self.conics),
                                             P(p["opacities"]), P(self.records), P(self.cum), P(self.background),
                                             P(self.final_Ts), P(self.final_idx),
                                             P(self.v_img), None, P(self.grad_rows), P(self.v_xy), P(self.v_conic),

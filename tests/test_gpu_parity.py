@@ -239,6 +239,35 @@ def test_culled_binning_is_the_generic_lists_minus_untouched_pairs(n, W, H, scal
         assert torch.equal(a, b)
 
 
+def test_tile_order_is_a_longest_first_permutation_and_changes_nothing():
+    """gsb_bucket_tile_ranges' tile order: a permutation of the tile ids in which list lengths never increase by more
+    than one 1/64 length bucket; image and gradients are bit-identical with and without it."""
+    n, W, H = 60_000, 640, 360
+    sc = _scene(n, W, H, 0.12, seed=31, opacity=(0.05, 0.9))
+    sc["means"][: n // 2, :2] *= 0.4                 # uneven coverage: long lists in the centre, short at the border
+    _, xys, depths, radii, conics, nth = _project_gpu(sc)
+    tb = ops.tile_bounds(W, H)
+    T = tb[0] * tb[1]
+    rng = np.random.default_rng(8)
+    colors, op = cu(rng.uniform(0, 1, (n, 3)).astype(np.float32)), cu(sc["opacities"])
+    bg = cu(np.zeros(3, np.float32))
+    m, max_len, bins, cum, stats, rec, _, _ = _bucket_exact(xys, depths, radii, conics, colors, op, tb, cull=True)
+    order = npy(bins.tile_order)
+    assert np.array_equal(np.sort(order), np.arange(T))
+    lens = (npy(bins)[:, 1] - npy(bins)[:, 0])[order]
+    bucket = lens.astype(np.int64) * 64 // (max_len + 1)
+    assert np.all(np.diff(bucket) <= 0) and lens[0] == max_len
+    a = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins, rec, bg, stats)                      # ordered (default)
+    b = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins.clone(), rec, bg, stats)              # identity order
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    v = cu(rng.uniform(-1, 1, (H, W, 3)).astype(np.float32))
+    g1 = ops.rasterize_backward(H, W, n, m, bins, conics, op, rec, cum, bg, a[1], a[2], v, tile_order=bins.tile_order)
+    g2 = ops.rasterize_backward(H, W, n, m, bins, conics, op, rec, cum, bg, a[1], a[2], v)
+    for x, y in zip(g1, g2):
+        assert torch.equal(x, y)
+
+
 def test_binning_capacity_overflow_is_flagged_and_harmless():
     """Capacities smaller than the frame needs: stats[2] = 1 and neither the sort/pack nor the blend kernel touch
     their outputs; the operator redoes the frame with larger capacities and gives the same image."""
@@ -263,7 +292,7 @@ def test_binning_capacity_overflow_is_flagged_and_harmless():
         assert bool((rec2 == 0xAB).all())
         out = torch.full((H, W, 3), -7.0, device=DEV)
         fT, fI = torch.empty((H, W), device=DEV), torch.empty((H, W), dtype=torch.int32, device=DEV)
-        capi.check(capi.lib().gsb_rasterize_forward_packed(H, W, tb[0], tb[1], m_cap, capi.ptr(b2), capi.ptr(st2),
+        capi.check(capi.lib().gsb_rasterize_forward_packed(H, W, tb[0], tb[1], m_cap, capi.ptr(b2), None, capi.ptr(st2),
                                                            capi.ptr(bg), capi.ptr(rec2), capi.ptr(out), capi.ptr(fT),
                                                            capi.ptr(fI), capi.stream()))
         assert bool((out == -7.0).all())
