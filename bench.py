@@ -30,11 +30,11 @@ WORKLOADS = {
 
 
 # kernels of OURS launched per fwd+bwd step (counted from the C-ABI implementations, fast binning path):
-#   sh_fwd(+clamp) 1, project_fwd 1, bin_count 1, count_scan 1, tile_scan 1, bucket_emit 1, tile_dsort_pack 1,
+#   sh_fwd(+clamp) 1, project_fwd 1, bin_count 1, count_scan 1, tile_scan 1, tile_order 1, bucket_emit 1, tile_dsort_pack 1,
 #   tile_sort_pack (fallback pass) 1, blend_fwd 1, mse 1, blend_bwd 1, row_reduce 1, project_bwd 1, sh_bwd 1
 #   (N>1 fused exchange: mask 1 + exchange 1 instead of sh_bwd; the two cross-rank barriers are torch's kernels)
 def launches_per_step(world=1, fused=True, train=False):
-    n = 13 + (2 if (world > 1 and fused) else 1)
+    n = 14 + (2 if (world > 1 and fused) else 1)
     return n + (1 if train else 0)
 
 

@@ -440,19 +440,39 @@ __device__ __forceinline__ void write_tile_records(const u64 *__restrict__ sorte
                                                    const GsbRecord *__restrict__ gattr,
                                                    GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
                                                    int *__restrict__ gaussian_ids_sorted) {
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        const int k = (int)(unsigned)(sorted[i] & 0xffffffffull);
-        const int g = gaussian_ids[k];
-        const float4 *src = reinterpret_cast<const float4 *>(gattr + g);   // 3 x 128-bit gather (L2-resident)
-        float4 q0 = __ldg(src);
-        const float4 q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-        q0.w = __int_as_float(k);
-        float4 *dst = reinterpret_cast<float4 *>(records + first + i);
-        stg_stream4(dst, q0);
-        stg_stream4(dst + 1, q1);
-        stg_stream4(dst + 2, q2);
-        if (sorted_index) sorted_index[first + i] = k;
-        if (gaussian_ids_sorted) gaussian_ids_sorted[first + i] = g;
+    // The chain composite -> slot k -> Gaussian id -> attribute record is three dependent (L2 / DRAM) gathers per entry:
+    // four entries per thread are walked in lock-step so that four independent chains are in flight.
+    constexpr int U = 4;
+    for (int i0 = threadIdx.x; i0 < L; i0 += U * blockDim.x) {
+        int k[U], g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            k[u] = (i < L) ? (int)(unsigned)(sorted[i] & 0xffffffffull) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) g[u] = (k[u] >= 0) ? __ldg(gaussian_ids + k[u]) : 0;
+        float4 q0[U], q1[U], q2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (k[u] >= 0) {
+                const float4 *src = reinterpret_cast<const float4 *>(gattr + g[u]);   // 3 x 128-bit gather
+                q0[u] = __ldg(src); q1[u] = __ldg(src + 1); q2[u] = __ldg(src + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (k[u] >= 0) {
+                q0[u].w = __int_as_float(k[u]);
+                float4 *dst = reinterpret_cast<float4 *>(records + first + i);
+                stg_stream4(dst, q0[u]);
+                stg_stream4(dst + 1, q1[u]);
+                stg_stream4(dst + 2, q2[u]);
+                if (sorted_index) sorted_index[first + i] = k[u];
+                if (gaussian_ids_sorted) gaussian_ids_sorted[first + i] = g[u];
+            }
+        }
     }
 }
 
