@@ -441,8 +441,8 @@ __device__ __forceinline__ void write_tile_records(const u64 *__restrict__ sorte
                                                    GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
                                                    int *__restrict__ gaussian_ids_sorted) {
     // The chain composite -> slot k -> Gaussian id -> attribute record is three dependent (L2 / DRAM) gathers per entry:
-    // four entries per thread are walked in lock-step so that four independent chains are in flight.
-    constexpr int U = 4;
+    // two entries per thread are walked in lock-step so that two independent chains are in flight (more costs occupancy).
+    constexpr int U = 2;
     for (int i0 = threadIdx.x; i0 < L; i0 += U * blockDim.x) {
         int k[U], g[U];
 #pragma unroll
