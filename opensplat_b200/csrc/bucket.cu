@@ -435,14 +435,16 @@ __device__ __forceinline__ void cta_radix_sort_depth(u64 *buf, unsigned (*whist)
 }
 
 // Gather + pack of one tile: record i of the tile = attributes of the Gaussian behind the i-th sorted composite.
+template <int U>
 __device__ __forceinline__ void write_tile_records(const u64 *__restrict__ sorted, int L, int first,
                                                    const int *__restrict__ gaussian_ids,
                                                    const GsbRecord *__restrict__ gattr,
                                                    GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
                                                    int *__restrict__ gaussian_ids_sorted) {
-    // The chain composite -> slot k -> Gaussian id -> attribute record is three dependent (L2 / DRAM) gathers per entry:
-    // two entries per thread are walked in lock-step so that two independent chains are in flight (more costs occupancy).
-    constexpr int U = 2;
+    // The chain composite -> slot k -> Gaussian id -> attribute record is three dependent (L2 / DRAM) gathers per entry;
+    // U entries per thread are walked in lock-step so that U independent chains are in flight.  U = 2 pays when shared
+    // memory already limits the resident CTAs (long lists, C5: 1.53 -> 1.03 ms for the stage); with short lists the
+    // extra registers cost more occupancy than the second chain brings (C2: 0.144 -> 0.191 ms), so U = 1 there.
     for (int i0 = threadIdx.x; i0 < L; i0 += U * blockDim.x) {
         int k[U], g[U];
 #pragma unroll
@@ -482,6 +484,7 @@ __device__ __forceinline__ void write_tile_records(const u64 *__restrict__ sorte
 // network -- at C5's ~1000-entry lists an order of magnitude fewer instructions.  The result is the same total order
 // as any comparison sort of the composites.  A tile whose depths cluster (some bin above DS_BIN_LIMIT entries, or all
 // depths equal) is left to K4b (tile_done[tile] = 0), which also handles lists longer than this kernel's capacity.
+template <int U>
 __global__ void __launch_bounds__(256)
 tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
                        const int *__restrict__ gaussian_ids, const GsbRecord *__restrict__ gattr,
@@ -511,7 +514,7 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
             out[32 + lane] = b;
         }
         __syncthreads();
-        write_tile_records(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
+        write_tile_records<U>(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
         if (threadIdx.x == 0) tile_done[tile] = 1;
         return;
     }
@@ -576,7 +579,7 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
         }
     }
     __syncthreads();
-    write_tile_records(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
+    write_tile_records<U>(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
     if (threadIdx.x == 0) tile_done[tile] = 1;
 }
 
@@ -676,7 +679,7 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
         }
         __syncthreads();
     }
-    write_tile_records(skey, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
+    write_tile_records<1>(skey, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
 }
 
 struct BucketLayout {
@@ -793,12 +796,18 @@ extern "C" int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, con
         const int dcap = cap < 8192 ? cap : 8192;
         const size_t dsmem = (size_t)dcap * 16;
         tile_done = (unsigned char *)(ws + L.done);
-        if (dsmem > 32 * 1024)
-            GSB_CUDA(cudaFuncSetAttribute(tile_dsort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)dsmem));
-        tile_dsort_pack_kernel<<<T, 256, dsmem, s>>>(dcap, reinterpret_cast<const int2 *>(tile_bins), comp, gids,
-                                                    gattr, reinterpret_cast<GsbRecord *>(records), sorted_index,
-                                                    gaussian_ids_sorted, stats, tile_done);
+#define GSB_DSP(U)                                                                                              \
+    do {                                                                                                        \
+        if (dsmem > 32 * 1024)                                                                                  \
+            GSB_CUDA(cudaFuncSetAttribute(tile_dsort_pack_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)dsmem));                                                         \
+        tile_dsort_pack_kernel<U><<<T, 256, dsmem, s>>>(dcap, reinterpret_cast<const int2 *>(tile_bins), comp, gids, \
+                                                       gattr, reinterpret_cast<GsbRecord *>(records), sorted_index, \
+                                                       gaussian_ids_sorted, stats, tile_done);                  \
+    } while (0)
+        if (dcap <= 1024) GSB_DSP(1);
+        else GSB_DSP(2);
+#undef GSB_DSP
     }
     const size_t smem = (size_t)cap * 8;
 #define GSB_TSP(MAXI)                                                                                           \

@@ -220,7 +220,7 @@ sh_backward_kernel(int n, int degrees_to_use, const float *__restrict__ viewdirs
 // every thread expands its own Gaussian.
 //
 // The same launch also carries the all-reduce of the remaining per-Gaussian gradients (means, scales, quats,
-// opacity: the `geom` prefix of the flat gradient buffer, 44 B/Gaussian): the first `geom_blocks` CTAs run a
+// opacity: the `geom` prefix of the flat gradient buffer, 44 B/Gaussian): the first `geom_blocks` (4 x SMs) CTAs run a
 // two-shot all-reduce in which rank r owns slice r -- with NVSwitch multicast (`geom_mc` != NULL) one
 // multimem.ld_reduce pulls the sum of all ranks' copies through the switch and one multimem.st broadcasts the
 // result to every rank; without multicast the slice is summed from / written to the peers' mapped pointers.
@@ -255,10 +255,19 @@ sh_backward_multiview_kernel(int n, int degrees_to_use, const float *__restrict_
         const long long lo = chunk * rank, hi = min(geom_vec4, lo + chunk);
         const long long stride = (long long)geom_blocks * SH_THREADS;
         if (geom_mc != nullptr) {
-            for (long long i = lo + (long long)blockIdx.x * SH_THREADS + threadIdx.x; i < hi; i += stride) {
-                float4 v = multimem_ld_reduce_add(geom_mc + 4 * i);
-                v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-                multimem_st(geom_mc + 4 * i, v);
+            // four independent switch reductions in flight per thread (each is a ~2-3 us NVLink round trip)
+            constexpr int GU = 4;
+            for (long long i0 = lo + (long long)blockIdx.x * SH_THREADS + threadIdx.x; i0 < hi; i0 += GU * stride) {
+                float4 v[GU];
+#pragma unroll
+                for (int u = 0; u < GU; ++u)
+                    if (i0 + u * stride < hi) v[u] = multimem_ld_reduce_add(geom_mc + 4 * (i0 + u * stride));
+#pragma unroll
+                for (int u = 0; u < GU; ++u)
+                    if (i0 + u * stride < hi) {
+                        v[u].x *= scale; v[u].y *= scale; v[u].z *= scale; v[u].w *= scale;
+                        multimem_st(geom_mc + 4 * (i0 + u * stride), v[u]);
+                    }
             }
         } else {
             for (long long i = lo + (long long)blockIdx.x * SH_THREADS + threadIdx.x; i < hi; i += stride) {
@@ -488,7 +497,7 @@ static int launch_multiview(int n, int degree, int degrees_to_use, const float *
         GSB_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (geom_floats % 4) == 0);
         GSB_CHECK_ARG(geom_multicast || (geom_per_rank && world <= MV_MAX_RANKS));
         GSB_CHECK_ARG(((uintptr_t)geom_multicast % 16) == 0);
-        geom_blocks = 2 * gsb_sm_count_sh();
+        geom_blocks = 4 * gsb_sm_count_sh();
     }
     if (n == 0 && geom_blocks == 0) return 0;
     GSB_CHECK_ARG(n == 0 || (means && cam_positions && v_rgbs_per_view && v_coeffs));

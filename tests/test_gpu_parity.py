@@ -256,7 +256,7 @@ def test_tile_order_is_a_longest_first_permutation_and_changes_nothing():
     assert np.array_equal(np.sort(order), np.arange(T))
     lens = (npy(bins)[:, 1] - npy(bins)[:, 0])[order]
     bucket = lens.astype(np.int64) * 64 // (max_len + 1)
-    assert np.all(np.diff(bucket) <= 0) and lens[0] == max_len
+    assert np.all(np.diff(bucket) <= 0) and bucket[0] == bucket.max() and lens.max() == max_len
     a = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins, rec, bg, stats)                      # ordered (default)
     b = ops.rasterize_forward_packed(tb, (W, H, 1), m, bins.clone(), rec, bg, stats)              # identity order
     for x, y in zip(a, b):
