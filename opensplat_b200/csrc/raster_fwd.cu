@@ -147,6 +147,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 const float adx2 = q1.x * dx * dx;   // (a/2) dx^2
                 const float bdx = q1.y * dx;
                 const float dy0 = q0.y - py0;
+                const int idx = idx0 + t;   // sorted index of this record (final_idx of the pixels it is the last to blend)
                 // visit only the slots jlo..jhi (contiguous) inside the record's y-extent; warp-uniform control
                 // flow.  Two code shapes, chosen per kernel by A/B measurement: a computed jump into the slot
                 // sequence (GSB_*_SLOT_SWITCH=1), or a straight line of per-slot bit tests that leaves after jhi.
@@ -171,7 +172,7 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                     cg[j] = fmaf(q2.y, vis, cg[j]);                                                       \
                     cb[j] = fmaf(q2.z, vis, cb[j]);                                                       \
                     T[j] = next_T;                                                                        \
-                    last[j] = idx0 + t;                                                                   \
+                    last[j] = idx;                                                                        \
                     if (COUNT) ++n_blend;                                                                 \
                 }                                                                                         \
             }                                                                                             \

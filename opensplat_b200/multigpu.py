@@ -3,7 +3,10 @@
 Baseline (parallel.allreduce_gradients): every rank runs sh_backward and then ONE NCCL all-reduce over the
 flat 59-float/Gaussian gradient buffer (236 MB at 1M Gaussians, SH degree 3).
 
-Fused path (this module), ONE kernel launch per step (`gsb_exchange_gradients`) between two cross-rank barriers:
+Fused path (this module): the same kernel (`sh_backward_multiview_kernel`, two CTA roles) either as ONE launch per step
+(`exchange()`: `gsb_exchange_gradients` between two cross-rank barriers) or, in the pipeline, as its two roles on two
+streams (`start_colour()` right after rasterize-backward, `finish()` after project-backward) so that the colour pulls
+overlap project_backward and the geometry all-reduce:
  * the SH VJP is rank-1 in (view basis) x (colour gradient), so instead of reducing the 48 coefficient gradients
    per Gaussian every rank exposes only its view's colour gradient v_rgb [N,3] in symmetric (peer-mapped) memory
    and the kernel forms sum_r Y_r (x) v_rgb_r itself, pulling the peers' v_rgb over NVLink with coalesced loads
@@ -38,6 +41,9 @@ class ViewParallelExchange:
         dist.all_gather(allcp, cp, group=self.group)
         self.cam_positions = torch.cat(allcp, 0).contiguous()
         self.use_multicast = os.environ.get("GSB_EXCHANGE_MULTICAST", "1") != "0"
+        self.overlap = os.environ.get("GSB_EXCHANGE_OVERLAP", "1") != "0"
+        self.side = torch.cuda.Stream(device=dev)
+        self._rgb_ready, self._colour_done = torch.cuda.Event(), torch.cuda.Event()
         self._alloc_symmetric(pipe)
 
     def _alloc_symmetric(self, pipe):
@@ -74,9 +80,44 @@ class ViewParallelExchange:
         """Where this step's rasterize-backward must write its colour gradient."""
         return self.v_rgb
 
+    def start_colour(self, average=True):
+        """Call right after rasterize-backward (v_rgb is final, the geometry gradients are not yet): masks v_rgb with
+        the clamp's gradient and starts the multi-view SH backward -- the part of the exchange that moves most bytes,
+        (G-1) x 12 B per Gaussian -- on a side stream, so that it overlaps project_backward and, afterwards, the
+        all-reduce of the geometry gradients."""
+        p = self.pipe
+        L = capi.lib()
+        self._scale = 1.0 / self.world if average else 1.0
+        cur = torch.cuda.current_stream()
+        capi.check(L.gsb_mask_rgb_grad(p.n, capi.ptr(p.rgbs), capi.ptr(self.v_rgb), capi.stream()))
+        self._rgb_ready.record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self._rgb_ready)
+            self.hdl.barrier(channel=0)          # every rank's v_rgb is complete
+            capi.check(L.gsb_sh_backward_multiview(
+                p.n, p.deg, p.deg, capi.ptr(p.p["means"]), self.world, capi.ptr(self.cam_positions),
+                self.rgb_ptrs.data_ptr(), self._scale, capi.ptr(p.g["coeffs"]), self.side.cuda_stream))
+            self._colour_done.record(self.side)
+
+    def finish(self):
+        """Call after project_backward: all-reduces the geometry gradients (two-shot; NVSwitch multimem when mapped),
+        joins the colour half and closes the step with the barrier that lets every rank overwrite its buffers."""
+        p = self.pipe
+        L = capi.lib()
+        self.hdl.barrier(channel=1)              # every rank's geometry gradients are complete
+        capi.check(L.gsb_exchange_gradients(
+            0, p.deg, p.deg, None, 1, capi.ptr(self.cam_positions), None, self._scale, None, self.rank, self.world,
+            self.geom_numel, self.geom_ptrs.data_ptr(), self.multicast_ptr if self.multicast_ptr else None,
+            capi.stream()))
+        torch.cuda.current_stream().wait_event(self._colour_done)
+        # every rank's slice of the reduced geometry gradients has landed everywhere, and nobody still reads the v_rgb /
+        # geometry buffers of this step (so the next backward pass may overwrite them)
+        self.hdl.barrier(channel=2)
+
     def exchange(self, average=True):
-        """Call after project_backward: masks v_rgb with the clamp's gradient, then one fused launch does the
-        multi-view SH backward (peer pulls over NVLink) and the all-reduce of the geometry gradients."""
+        """The whole exchange after project_backward, as ONE fused launch (gsb_exchange_gradients: both CTA roles in one
+        grid) between two barriers -- no overlap with the backward kernels; what callers use that cannot split the
+        step (bench.py's operator-level e2e arm)."""
         p = self.pipe
         L = capi.lib()
         scale = 1.0 / self.world if average else 1.0
@@ -87,6 +128,4 @@ class ViewParallelExchange:
             p.n, p.deg, p.deg, capi.ptr(p.p["means"]), self.world, capi.ptr(self.cam_positions),
             self.rgb_ptrs.data_ptr(), scale, capi.ptr(p.g["coeffs"]), self.rank, self.world, self.geom_numel,
             self.geom_ptrs.data_ptr(), self.multicast_ptr if self.multicast_ptr else None, capi.stream()))
-        # every rank's slice of the reduced geometry gradients has landed everywhere, and nobody still reads the
-        # v_rgb / geometry buffers of this step (so the next backward pass may overwrite them)
-        self.hdl.barrier(channel=0)
+        self.hdl.barrier(channel=2)

@@ -276,6 +276,8 @@ class SplatPipeline:
                                             P(self.final_Ts), P(self.final_idx),
                                             P(self.v_img), None, P(self.grad_rows), P(self.v_xy), P(self.v_conic),
                                             P(v_rgbs), P(g["opacities"]), s))
+        if self.exchange is not None and self.exchange.overlap:
+            self.exchange.start_colour(average=True)   # colour pulls + SH expansion start now, on a side stream
         self._stage("project_bwd")
         capi.check(L.gsb_project_backward(n, P(p["means"]), P(p["scales"]), 1.0, P(p["quats"]), P(self.viewmat),
                                           P(self.projmat), fx, fy, cx, cy, H, W, None, P(self.radii), P(self.conics),
@@ -284,7 +286,10 @@ class SplatPipeline:
         self._stage("sh_bwd")
         if self.exchange is not None:
             # data-parallel: SH VJP fused with the cross-GPU exchange (also all-reduces the geometry grads)
-            self.exchange.exchange(average=True)
+            if self.exchange.overlap:
+                self.exchange.finish()
+            else:
+                self.exchange.exchange(average=True)
         else:
             # SH VJP with the gradient of the clamp fused (mask = forward rgbs > 0)
             capi.check(L.gsb_sh_backward_rgb(n, self.deg, self.deg, P(self.viewdirs), P(self.rgbs), P(self.v_rgbs),
