@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256)
 bucket_emit_kernel(int n, const GsbRecord *__restrict__ gattr, const float *__restrict__ depths,
                    const int *__restrict__ radii, const int *__restrict__ cum_tiles_hit, int cull, int tiles_x,
                    int tiles_y, int *__restrict__ cursor, unsigned long long *__restrict__ comp,
-                   int *__restrict__ gaussian_ids, const int *__restrict__ stats) {
+                   int *__restrict__ gaussian_ids, int *__restrict__ gid_at_pos, const int *__restrict__ stats) {
     if (stats[2]) return;   // capacities exceeded: the host redoes the frame
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -305,7 +305,8 @@ bucket_emit_kernel(int n, const GsbRecord *__restrict__ gattr, const float *__re
                 continue;
             const int pos = atomicAdd(&cursor[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
             comp[pos] = hi | (unsigned)k;
-            gaussian_ids[k] = i;
+            gid_at_pos[pos] = i;      // payload of the distribution sort (K4a): saves it the slot -> Gaussian gather
+            gaussian_ids[k] = i;      // slot -> Gaussian (K4b and the optional gaussian_ids_sorted output)
             ++k;
         }
 }
@@ -484,14 +485,51 @@ __device__ __forceinline__ void write_tile_records(const u64 *__restrict__ sorte
 // network -- at C5's ~1000-entry lists an order of magnitude fewer instructions.  The result is the same total order
 // as any comparison sort of the composites.  A tile whose depths cluster (some bin above DS_BIN_LIMIT entries, or all
 // depths equal) is left to K4b (tile_done[tile] = 0), which also handles lists longer than this kernel's capacity.
+// Pack of one tile whose sorted composites come with their Gaussian ids (the distribution sort's payload): one
+// dependent gather per entry (the attribute record) instead of two.
+template <int U>
+__device__ __forceinline__ void write_tile_records_g(const u64 *__restrict__ sorted, const int *__restrict__ sorted_g,
+                                                     int L, int first, const GsbRecord *__restrict__ gattr,
+                                                     GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
+                                                     int *__restrict__ gaussian_ids_sorted) {
+    for (int i0 = threadIdx.x; i0 < L; i0 += U * blockDim.x) {
+        float4 q0[U], q1[U], q2[U];
+        int k[U], g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < L) {
+                k[u] = (int)(unsigned)(sorted[i] & 0xffffffffull);
+                g[u] = sorted_g[i];
+                const float4 *src = reinterpret_cast<const float4 *>(gattr + g[u]);   // 3 x 128-bit gather
+                q0[u] = __ldg(src); q1[u] = __ldg(src + 1); q2[u] = __ldg(src + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < L) {
+                q0[u].w = __int_as_float(k[u]);
+                float4 *dst = reinterpret_cast<float4 *>(records + first + i);
+                stg_stream4(dst, q0[u]);
+                stg_stream4(dst + 1, q1[u]);
+                stg_stream4(dst + 2, q2[u]);
+                if (sorted_index) sorted_index[first + i] = k[u];
+                if (gaussian_ids_sorted) gaussian_ids_sorted[first + i] = g[u];
+            }
+        }
+    }
+}
+
 template <int U>
 __global__ void __launch_bounds__(256)
 tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
-                       const int *__restrict__ gaussian_ids, const GsbRecord *__restrict__ gattr,
-                       GsbRecord *__restrict__ records, int *__restrict__ sorted_index,
-                       int *__restrict__ gaussian_ids_sorted, const int *__restrict__ stats,
-                       unsigned char *__restrict__ tile_done) {
-    extern __shared__ unsigned long long dkey[];   // [cap] staged composites, [cap] scatter target
+                       const int *__restrict__ gid_at_pos, const int *__restrict__ gaussian_ids,
+                       const GsbRecord *__restrict__ gattr, GsbRecord *__restrict__ records,
+                       int *__restrict__ sorted_index, int *__restrict__ gaussian_ids_sorted,
+                       const int *__restrict__ stats, unsigned char *__restrict__ tile_done) {
+    // [cap] staged composites, [cap] scatter target, then the same two arrays for the payload (Gaussian ids)
+    extern __shared__ unsigned long long dkey[];
     __shared__ int dhist[DS_MAX_BINS];             // bin sizes, then write cursors, finally bin ends
     __shared__ int ds_scan[256 / 32 + 1];
     __shared__ unsigned ds_lo, ds_hi;
@@ -504,7 +542,8 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
     if (L <= 0) { if (threadIdx.x == 0) tile_done[tile] = 1; return; }
     if (L > cap) { if (threadIdx.x == 0) tile_done[tile] = 0; return; }
     u64 *in = dkey, *out = dkey + cap;
-    if (L <= 64) {   // tiny lists: one warp, bitonic network in registers / shuffles
+    int *gin = reinterpret_cast<int *>(dkey + 2 * cap), *gout = gin + cap;
+    if (L <= 64) {   // tiny lists: one warp, bitonic network in registers / shuffles (ids via the slot -> Gaussian table)
         if (threadIdx.x < 32) {
             u64 a = (lane < L) ? comp[range.x + lane] : ~0ull;
             u64 b = (32 + lane < L) ? comp[range.x + 32 + lane] : ~0ull;
@@ -514,7 +553,7 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
             out[32 + lane] = b;
         }
         __syncthreads();
-        write_tile_records<U>(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
+        write_tile_records<1>(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
         if (threadIdx.x == 0) tile_done[tile] = 1;
         return;
     }
@@ -527,6 +566,7 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const u64 c = comp[range.x + i];
         in[i] = c;
+        gin[i] = gid_at_pos[range.x + i];
         const unsigned d = (unsigned)(c >> 32);
         lo = min(lo, d); hi = max(hi, d);
     }
@@ -566,20 +606,24 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
     if (ds_maxbin > DS_BIN_LIMIT) { if (threadIdx.x == 0) tile_done[tile] = 0; return; }   // (uniform) clustered depths
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const u64 c = in[i];
-        out[atomicAdd(&dhist[bin_of(c)], 1)] = c;
+        const int p = atomicAdd(&dhist[bin_of(c)], 1);
+        out[p] = c;
+        gout[p] = gin[i];
     }
     __syncthreads();
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
         const int e = dhist[b], st = b ? dhist[b - 1] : 0;
-        for (int p = st + 1; p < e; ++p) {   // insertion sort by (depth bits, k)
+        for (int p = st + 1; p < e; ++p) {   // insertion sort by (depth bits, k), the Gaussian id moves along
             const u64 c = out[p];
+            const int cg = gout[p];
             int q = p - 1;
-            while (q >= st && out[q] > c) { out[q + 1] = out[q]; --q; }
+            while (q >= st && out[q] > c) { out[q + 1] = out[q]; gout[q + 1] = gout[q]; --q; }
             out[q + 1] = c;
+            gout[q + 1] = cg;
         }
     }
     __syncthreads();
-    write_tile_records<U>(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
+    write_tile_records_g<U>(out, gout, L, range.x, gattr, records, sorted_index, gaussian_ids_sorted);
     if (threadIdx.x == 0) tile_done[tile] = 1;
 }
 
@@ -683,7 +727,7 @@ tile_sort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigne
 }
 
 struct BucketLayout {
-    size_t hdr, state_n, state_t, cursor, zero_bytes, gattr, comp, gids, done, total;
+    size_t hdr, state_n, state_t, cursor, zero_bytes, gattr, comp, gids, gpos, done, total;
     int nblk_n, nblk_t;
 };
 BucketLayout bucket_layout(int n, int m, int T) {
@@ -699,6 +743,7 @@ BucketLayout bucket_layout(int n, int m, int T) {
     L.gattr = o; o += gsb_align_up((size_t)n * sizeof(GsbRecord), 256);
     L.comp = o; o += gsb_align_up((size_t)m * 8, 256);
     L.gids = o; o += gsb_align_up((size_t)m * 4, 256);
+    L.gpos = o; o += gsb_align_up((size_t)m * 4, 256);
     L.done = o; o += gsb_align_up((size_t)(T > 0 ? T : 1), 256);   // per tile: ordered + packed by K4a
     L.total = o;
     return L;
@@ -788,21 +833,23 @@ extern "C" int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, con
     int *gids = (int *)(ws + L.gids);
     GsbRecord *gattr = (GsbRecord *)(ws + L.gattr);
     bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, gattr, depths, radii, cum_tiles_hit, cull, tiles_x,
-                                                         tiles_y, (int *)(ws + L.cursor), comp, gids, stats);
+                                                         tiles_y, (int *)(ws + L.cursor), comp, gids,
+                                                         (int *)(ws + L.gpos), stats);
     // K4a (distribution sort) stages the list twice in shared memory; lists beyond its capacity, and tiles whose
     // depths cluster, are left to K4b (comparison sorts)
     unsigned char *tile_done = nullptr;
     if (GSB_DSORT) {
         const int dcap = cap < 8192 ? cap : 8192;
-        const size_t dsmem = (size_t)dcap * 16;
+        const size_t dsmem = (size_t)dcap * 24;   // 2 x 8 B composites + 2 x 4 B Gaussian ids per entry
         tile_done = (unsigned char *)(ws + L.done);
 #define GSB_DSP(U)                                                                                              \
     do {                                                                                                        \
         if (dsmem > 32 * 1024)                                                                                  \
             GSB_CUDA(cudaFuncSetAttribute(tile_dsort_pack_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)dsmem));                                                         \
-        tile_dsort_pack_kernel<U><<<T, 256, dsmem, s>>>(dcap, reinterpret_cast<const int2 *>(tile_bins), comp, gids, \
-                                                       gattr, reinterpret_cast<GsbRecord *>(records), sorted_index, \
+        tile_dsort_pack_kernel<U><<<T, 256, dsmem, s>>>(dcap, reinterpret_cast<const int2 *>(tile_bins), comp,  \
+                                                       (const int *)(ws + L.gpos), gids, gattr,                 \
+                                                       reinterpret_cast<GsbRecord *>(records), sorted_index,    \
                                                        gaussian_ids_sorted, stats, tile_done);                  \
     } while (0)
         if (dcap <= 1024) GSB_DSP(1);
