@@ -305,7 +305,7 @@ bucket_emit_kernel(int n, const GsbRecord *__restrict__ gattr, const float *__re
                 continue;
             const int pos = atomicAdd(&cursor[(size_t)(ty * tiles_x + tx) * CUR_STRIDE], 1);
             comp[pos] = hi | (unsigned)k;
-            gid_at_pos[pos] = i;      // payload of the distribution sort (K4a): saves it the slot -> Gaussian gather
+            if (gid_at_pos) gid_at_pos[pos] = i;   // payload of the distribution sort of LONG lists (K4a<.., true>)
             gaussian_ids[k] = i;      // slot -> Gaussian (K4b and the optional gaussian_ids_sorted output)
             ++k;
         }
@@ -521,7 +521,11 @@ __device__ __forceinline__ void write_tile_records_g(const u64 *__restrict__ sor
     }
 }
 
-template <int U>
+// PAYLOAD = true (long lists): the Gaussian ids written by K3 at the tile-major positions travel through the sort as
+// payload, so the pack needs ONE dependent gather per entry (C5, same box: stage 1.60 -> 1.15 ms); with short lists the
+// slot -> Gaussian table is L2-resident and the extra scattered store in K3 + the payload moves cost more than the
+// shorter chain saves (C2: 0.142 -> 0.159 ms), so PAYLOAD = false there.
+template <int U, bool PAYLOAD>
 __global__ void __launch_bounds__(256)
 tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsigned long long *__restrict__ comp,
                        const int *__restrict__ gid_at_pos, const int *__restrict__ gaussian_ids,
@@ -566,7 +570,7 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const u64 c = comp[range.x + i];
         in[i] = c;
-        gin[i] = gid_at_pos[range.x + i];
+        if (PAYLOAD) gin[i] = gid_at_pos[range.x + i];
         const unsigned d = (unsigned)(c >> 32);
         lo = min(lo, d); hi = max(hi, d);
     }
@@ -608,22 +612,27 @@ tile_dsort_pack_kernel(int cap, const int2 *__restrict__ tile_bins, const unsign
         const u64 c = in[i];
         const int p = atomicAdd(&dhist[bin_of(c)], 1);
         out[p] = c;
-        gout[p] = gin[i];
+        if (PAYLOAD) gout[p] = gin[i];
     }
     __syncthreads();
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
         const int e = dhist[b], st = b ? dhist[b - 1] : 0;
         for (int p = st + 1; p < e; ++p) {   // insertion sort by (depth bits, k), the Gaussian id moves along
             const u64 c = out[p];
-            const int cg = gout[p];
+            const int cg = PAYLOAD ? gout[p] : 0;
             int q = p - 1;
-            while (q >= st && out[q] > c) { out[q + 1] = out[q]; gout[q + 1] = gout[q]; --q; }
+            while (q >= st && out[q] > c) {
+                out[q + 1] = out[q];
+                if (PAYLOAD) gout[q + 1] = gout[q];
+                --q;
+            }
             out[q + 1] = c;
-            gout[q + 1] = cg;
+            if (PAYLOAD) gout[q + 1] = cg;
         }
     }
     __syncthreads();
-    write_tile_records_g<U>(out, gout, L, range.x, gattr, records, sorted_index, gaussian_ids_sorted);
+    if (PAYLOAD) write_tile_records_g<U>(out, gout, L, range.x, gattr, records, sorted_index, gaussian_ids_sorted);
+    else write_tile_records<U>(out, L, range.x, gaussian_ids, gattr, records, sorted_index, gaussian_ids_sorted);
     if (threadIdx.x == 0) tile_done[tile] = 1;
 }
 
@@ -832,28 +841,29 @@ extern "C" int gsb_bucket_sort_pack(int n, int m_capacity, int len_capacity, con
     unsigned long long *comp = (unsigned long long *)(ws + L.comp);
     int *gids = (int *)(ws + L.gids);
     GsbRecord *gattr = (GsbRecord *)(ws + L.gattr);
+    const bool long_lists = GSB_DSORT && cap > 1024;   // K4a then carries the Gaussian ids as sort payload
     bucket_emit_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(n, gattr, depths, radii, cum_tiles_hit, cull, tiles_x,
                                                          tiles_y, (int *)(ws + L.cursor), comp, gids,
-                                                         (int *)(ws + L.gpos), stats);
+                                                         long_lists ? (int *)(ws + L.gpos) : nullptr, stats);
     // K4a (distribution sort) stages the list twice in shared memory; lists beyond its capacity, and tiles whose
     // depths cluster, are left to K4b (comparison sorts)
     unsigned char *tile_done = nullptr;
     if (GSB_DSORT) {
         const int dcap = cap < 8192 ? cap : 8192;
-        const size_t dsmem = (size_t)dcap * 24;   // 2 x 8 B composites + 2 x 4 B Gaussian ids per entry
+        const size_t dsmem = (size_t)dcap * (long_lists ? 24 : 16);   // 2 x 8 B composites (+ 2 x 4 B Gaussian ids) per entry
         tile_done = (unsigned char *)(ws + L.done);
-#define GSB_DSP(U)                                                                                              \
+#define GSB_DSP(U, PAY)                                                                                         \
     do {                                                                                                        \
         if (dsmem > 32 * 1024)                                                                                  \
-            GSB_CUDA(cudaFuncSetAttribute(tile_dsort_pack_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)dsmem));                                                         \
-        tile_dsort_pack_kernel<U><<<T, 256, dsmem, s>>>(dcap, reinterpret_cast<const int2 *>(tile_bins), comp,  \
-                                                       (const int *)(ws + L.gpos), gids, gattr,                 \
-                                                       reinterpret_cast<GsbRecord *>(records), sorted_index,    \
-                                                       gaussian_ids_sorted, stats, tile_done);                  \
+            GSB_CUDA(cudaFuncSetAttribute(tile_dsort_pack_kernel<U, PAY>,                                       \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));            \
+        tile_dsort_pack_kernel<U, PAY><<<T, 256, dsmem, s>>>(dcap, reinterpret_cast<const int2 *>(tile_bins), comp, \
+                                                            (const int *)(ws + L.gpos), gids, gattr,            \
+                                                            reinterpret_cast<GsbRecord *>(records), sorted_index, \
+                                                            gaussian_ids_sorted, stats, tile_done);             \
     } while (0)
-        if (dcap <= 1024) GSB_DSP(1);
-        else GSB_DSP(2);
+        if (long_lists) GSB_DSP(2, true);
+        else GSB_DSP(1, false);
 #undef GSB_DSP
     }
     const size_t smem = (size_t)cap * 8;
