@@ -7,6 +7,7 @@
 // moves its 128 Gaussians' coefficients as one contiguous span with 128-bit streaming accesses
 // (fully coalesced, L1 bypassed) through a padded shared-memory transpose; rows are padded to
 // 4*odd floats so the per-thread 128-bit row reads are bank-conflict free.
+#include <stdlib.h>
 #include "gsb_common.cuh"
 
 static int gsb_sm_count_sh() {
@@ -486,6 +487,18 @@ extern "C" int gsb_mask_rgb_grad(int n, const float *rgbs, float *v_rgbs, gsb_st
     return 0;
 }
 
+// CTAs per SM of the all-reduce role (GSB_GEOM_BLOCKS overrides the default for experiments)
+static int geom_blocks_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("GSB_GEOM_BLOCKS");
+        v = e ? atoi(e) : 4;
+        if (v < 1) v = 1;
+        if (v > 32) v = 32;
+    }
+    return v;
+}
+
 static int launch_multiview(int n, int degree, int degrees_to_use, const float *means, int num_views,
                             const float *cam_positions, const float *const *v_rgbs_per_view, float scale,
                             float *v_coeffs, int rank, int world, long long geom_floats, float *const *geom_per_rank,
@@ -497,7 +510,7 @@ static int launch_multiview(int n, int degree, int degrees_to_use, const float *
         GSB_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (geom_floats % 4) == 0);
         GSB_CHECK_ARG(geom_multicast || (geom_per_rank && world <= MV_MAX_RANKS));
         GSB_CHECK_ARG(((uintptr_t)geom_multicast % 16) == 0);
-        geom_blocks = 4 * gsb_sm_count_sh();
+        geom_blocks = geom_blocks_per_sm() * gsb_sm_count_sh();
     }
     if (n == 0 && geom_blocks == 0) return 0;
     GSB_CHECK_ARG(n == 0 || (means && cam_positions && v_rgbs_per_view && v_coeffs));

@@ -79,6 +79,20 @@ def main():
                 ex.rgb_ptrs.data_ptr(), 1.0, capi.ptr(pipe.g["coeffs"]), rank, world, ex.geom_numel,
                 ex.geom_ptrs.data_ptr(), ex.multicast_ptr if ex.multicast_ptr else None, capi.stream()))
 
+        def geom_only():
+            capi.check(L.gsb_exchange_gradients(
+                0, pipe.deg, pipe.deg, None, 1, capi.ptr(ex.cam_positions), None, 1.0, None, rank, world,
+                ex.geom_numel, ex.geom_ptrs.data_ptr(), ex.multicast_ptr if ex.multicast_ptr else None, capi.stream()))
+
+        def two_streams():     # the pipeline's form: colour half on a side stream, geometry half on the main one
+            cur = torch.cuda.current_stream()
+            ex.side.wait_stream(cur)
+            capi.check(L.gsb_sh_backward_multiview(n, pipe.deg, pipe.deg, capi.ptr(pipe.p["means"]), world,
+                                                   capi.ptr(ex.cam_positions), ex.rgb_ptrs.data_ptr(), 1.0,
+                                                   capi.ptr(pipe.g["coeffs"]), ex.side.cuda_stream))
+            geom_only()
+            cur.wait_stream(ex.side)
+
         def sh_only():
             capi.check(L.gsb_sh_backward_multiview(n, pipe.deg, pipe.deg, capi.ptr(pipe.p["means"]), world,
                                                    capi.ptr(ex.cam_positions), ex.rgb_ptrs.data_ptr(), 1.0,
@@ -90,6 +104,8 @@ def main():
         after = nvlink_kib(local) if rank == 0 else None
         k_only = timed(launch_only, a.reps)                               # (values grow; timing only)
         sh = timed(sh_only, a.reps)
+        go = timed(geom_only, a.reps)
+        ts = timed(two_streams, a.reps)
         bar = timed(lambda: ex.hdl.barrier(channel=0), a.reps)
         rgb_bytes = (world - 1) * 12 * n
         geom_bytes = ex.geom_numel * 4
@@ -97,6 +113,7 @@ def main():
         # G-1 peers) + the other ranks' reduced slices
         recv = rgb_bytes + (geom_bytes if flavour == "multimem" else geom_bytes // world * (world - 1) * 2)
         r = {"step_ms_mask_barrier_launch_barrier": full, "launch_only_ms": k_only, "sh_half_only_ms": sh,
+             "geometry_half_only_ms": go, "two_streams_ms": ts, "geom_blocks_per_sm": os.environ.get("GSB_GEOM_BLOCKS", "4"),
              "barrier_ms": bar, "bytes_received_per_rank_model": recv,
              "nvlink_GBps_achieved_launch_only": recv / (k_only * 1e-3) / 1e9,
              "nvlink_GBps_colour_pull_only": rgb_bytes / (sh * 1e-3) / 1e9,
