@@ -510,7 +510,14 @@ static int launch_multiview(int n, int degree, int degrees_to_use, const float *
         GSB_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (geom_floats % 4) == 0);
         GSB_CHECK_ARG(geom_multicast || (geom_per_rank && world <= MV_MAX_RANKS));
         GSB_CHECK_ARG(((uintptr_t)geom_multicast % 16) == 0);
-        geom_blocks = geom_blocks_per_sm() * gsb_sm_count_sh();
+        // about two rounds of four 16-byte reductions per thread; between 1 and 8 CTAs per SM.  (8 GPUs, 1M Gaussians:
+        // the role is bound by the switch, 0.10 ms for the 44 MB at any CTA count from 1 to 16 per SM, and fewer CTAs leave
+        // more slots to the colour half: profiles/r02_exchange_n8_geom_sweep.json)
+        const int sms = gsb_sm_count_sh();
+        const long long slice = (geom_floats / 4 + world - 1) / world;
+        long long want = (slice + 2 * 4 * SH_THREADS - 1) / (2 * 4 * SH_THREADS);
+        if (getenv("GSB_GEOM_BLOCKS")) want = (long long)geom_blocks_per_sm() * sms;
+        geom_blocks = (int)(want < sms ? sms : (want > 8LL * sms ? 8LL * sms : want));
     }
     if (n == 0 && geom_blocks == 0) return 0;
     GSB_CHECK_ARG(n == 0 || (means && cam_positions && v_rgbs_per_view && v_coeffs));
