@@ -208,6 +208,14 @@ def _traffic_for(workload, kernel):
         return None
 
 
+def _ncu_counter(workload, kernel, key):
+    """Per-launch counter of this round's ncu capture of exactly this workload / kernel (profiles/ncu_counters.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json"))).get(workload, {}).get(kernel, {}).get(key)
+    except Exception:
+        return None
+
+
 def _roofline(pipe, stage_ms, ms_step, workload, pairs):
     peak, peak_src = peaks()
     alg, passes = pipe.algorithmic_bytes()
@@ -232,6 +240,12 @@ def _roofline(pipe, stage_ms, ms_step, workload, pairs):
         if b:   # the backward pass replays the same blended set (up to each pixel's final index)
             roof["pairs"]["bwd_blended_pairs_per_s"] = pairs["pairs_blended"] / (b * 1e-3)
             roof["pairs"]["bwd_evaluated_pairs_per_s"] = pairs["pairs_evaluated"] / (b * 1e-3)
+        # warp-instructions per blended pair: instruction totals from the committed ncu capture of THIS workload
+        # (null without one), pair count from this run
+        for key, st in (("fwd", "raster_fwd"), ("bwd", "raster_bwd")):
+            ins = _ncu_counter(workload, st, "warp_instructions")
+            roof["pairs"][f"{key}_warp_instructions_per_blended_pair"] = (ins / pairs["pairs_blended"]) if ins else None
+            roof["pairs"][f"{key}_warp_instructions_per_record"] = (ins / pairs["records_processed"]) if ins else None
     roof_path = {"achieved": path_ach, "peak": peak, "unit": "GB/s", "frac": path_ach / peak,
                  "algorithmic_bytes_per_step": path_bytes, "generic_sort_passes_modelled": passes}
     return roof, roof_path

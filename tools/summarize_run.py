@@ -65,7 +65,7 @@ def launches():
 
 
 def ncu_reps():
-    traffic = {}
+    traffic, counters = {}, {}
     tfile = os.path.join(P, "dram_traffic.json")
     for f, wl in ((os.path.join(G, "r2_prof_c2.ncu-rep"), "c2_1M_1080p_sh3"),
                   (os.path.join(G, "r2_prof_c5.ncu-rep"), "c5_5M_1440p_dense")):
@@ -91,6 +91,13 @@ def ncu_reps():
             st = next((s for k, s in STAGE_OF.items() if k in kn), None)
             if st and "dram__bytes_read.sum" in idx:
                 traffic.setdefault(wl, {})[st] = int(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"))
+            if st and "smsp__inst_executed.sum" in idx:
+                counters.setdefault(wl, {})[st] = {
+                    "warp_instructions": int(float(r[idx["smsp__inst_executed.sum"]].replace(",", ""))),
+                    "issue_active_pct": float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+                    "sm_throughput_pct": float(r[idx["sm__throughput.avg.pct_of_peak_sustained_elapsed"]])}
+    if counters:
+        json.dump(counters, open(os.path.join(P, "ncu_counters.json"), "w"), indent=1)
     if traffic:
         json.dump(traffic, open(tfile, "w"), indent=1)
         print("dram_traffic.json", traffic)
