@@ -37,6 +37,8 @@ extern "C" {
 #define GSB_ERR_INVALID_ARG (-1)
 #define GSB_ERR_WORKSPACE (-2)
 #define GSB_ERR_UNSUPPORTED (-3)
+/* flags of gsb_rasterize_forward_packed_ex / gsb_rasterize_backward_ex */
+#define GSB_RASTER_CLAMP_MAX_ONE 1u
 
 typedef void *gsb_stream_t; /* cudaStream_t */
 
@@ -122,6 +124,27 @@ int gsb_project_backward(int n, const float *means3d, const float *scales, float
                          const int32_t *radii, const float *conics, const float *v_xy,
                          const float *v_depth, const float *v_conic, float *v_mean3d, float *v_scale,
                          float *v_quat, gsb_stream_t stream);
+/* gsb_project_forward_activated / gsb_project_backward_activated: the same two kernels with the parameter
+ *   activations of Model::forward as their prologue / epilogue (model.cpp:148-150 `exp(scales)`,
+ *   `quats / quats.norm()`; model.cpp:200 `sigmoid(opacities)`) -- SURVEY.md 8f row 1.  Inputs are the RAW
+ *   parameters: log_scales [n,3], raw_quats [n,4] (the projection normalises the quaternion itself, as the
+ *   reference's quat_to_rotmat does, so the separate normalisation pass is simply dropped), opacity_logits [n].
+ *   Forward also writes opacities [n] = sigmoid(logits) for the rasterizer.  Backward takes that `opacities`
+ *   array and the rasterizer's v_opacity [n] (NULL == zeros) and returns gradients w.r.t. the raw parameters:
+ *   v_log_scales = v_scale * exp(log_scale), v_raw_quats, v_opacity_logits = v_opacity * o * (1 - o). */
+int gsb_project_forward_activated(int n, const float *means3d, const float *log_scales, float glob_scale,
+                                  const float *raw_quats, const float *opacity_logits, const float *viewmat,
+                                  const float *projmat, float fx, float fy, float cx, float cy, int img_h,
+                                  int img_w, int tiles_x, int tiles_y, float clip_thresh, float *cov3d, float *xys,
+                                  float *depths, int32_t *radii, float *conics, int32_t *num_tiles_hit,
+                                  float *opacities, gsb_stream_t stream);
+int gsb_project_backward_activated(int n, const float *means3d, const float *log_scales, float glob_scale,
+                                   const float *raw_quats, const float *opacities, const float *viewmat,
+                                   const float *projmat, float fx, float fy, int img_h, int img_w,
+                                   const int32_t *radii, const float *conics, const float *v_xy,
+                                   const float *v_depth, const float *v_conic, const float *v_opacity,
+                                   float *v_mean3d, float *v_log_scales, float *v_raw_quats,
+                                   float *v_opacity_logits, gsb_stream_t stream);
 
 /* ---- Tile binning ----------------------------------------------------------------------------
  * gsb_cumsum_tiles_hit replaces torch::cumsum(numTilesHit, 0, kInt32) (rasterize_gaussians.cpp:62).
@@ -226,6 +249,26 @@ int gsb_rasterize_backward_ordered(int img_h, int img_w, int tiles_x, int tiles_
                                    const float *background, const float *final_Ts, const int32_t *final_idx,
                                    const float *v_output, const float *v_output_alpha, void *grad_rows, float *v_xy,
                                    float *v_conic, float *v_colors, float *v_opacity, gsb_stream_t stream);
+/* gsb_pack_records: the packing half of gsb_rasterize_forward alone (sorted intersection list -> 48-B records).
+ * gsb_rasterize_forward_packed_ex / gsb_rasterize_backward_ex: gsb_rasterize_forward_packed /
+ *   gsb_rasterize_backward_ordered with `flags`.  GSB_RASTER_CLAMP_MAX_ONE fuses the caller's
+ *   `rgb = clamp_max(rgb, 1)` (model.cpp:222) into the blend epilogue: out_img is written clamped, the channels that
+ *   were cut are remembered in bits 28..30 of final_idx (so m must stay below 2^28 and final_idx is private to the
+ *   pair of calls), and the backward call -- given the gradient of the CLAMPED image -- passes no gradient through
+ *   them (torch's clamp_max mask `x <= max`). */
+int gsb_pack_records(int m, const int32_t *gaussian_ids_sorted, const int32_t *sorted_index, const float *xys,
+                     const float *conics, const float *colors, const float *opacities, void *records,
+                     gsb_stream_t stream);
+int gsb_rasterize_forward_packed_ex(int img_h, int img_w, int tiles_x, int tiles_y, int m, const int32_t *tile_bins,
+                                    const int32_t *tile_order, const int32_t *bin_stats, const float *background,
+                                    void *records, float *out_img, float *final_Ts, int32_t *final_idx,
+                                    unsigned flags, gsb_stream_t stream);
+int gsb_rasterize_backward_ex(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
+                              const int32_t *tile_bins, const int32_t *tile_order, const float *conics,
+                              const float *opacities, void *records, const int32_t *cum_tiles_hit,
+                              const float *background, const float *final_Ts, const int32_t *final_idx,
+                              const float *v_output, const float *v_output_alpha, void *grad_rows, float *v_xy,
+                              float *v_conic, float *v_colors, float *v_opacity, unsigned flags, gsb_stream_t stream);
 /* gsb_rasterize_forward_count: diagnostic twin of gsb_rasterize_forward_packed (same outputs) that also ACCUMULATES
  *   into pair_counts (device uint64[4]; zero it first) {records that pass the per-record extent test, slot visits
  *   (x 32 lanes = pixel tests), pixel pairs evaluated (sigma inside the extent: one ex2), pixel pairs blended} --

@@ -31,6 +31,13 @@ _SIGS = {
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_project_backward": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    # n, means, log_scales, glob, raw_quats, logits, view, proj, fx, fy, cx, cy, H, W, tx, ty, clip, 6 outputs, opac, stream
+    "gsb_project_forward_activated": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _f,
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    # n, means, log_scales, glob, raw_quats, opac, view, proj, fx, fy, H, W, radii, conics, v_xy, v_depth, v_conic,
+    # v_opacity, v_means, v_log_scales, v_raw_quats, v_logits, stream
+    "gsb_project_backward_activated": (_i, [_i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _f, _f, _i, _i,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_cumsum_workspace_bytes": (_sz, [_i]),
     "gsb_cumsum_tiles_hit": (_i, [_i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gsb_map_gaussian_to_intersects": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
@@ -50,6 +57,10 @@ _SIGS = {
     "gsb_rasterize_forward_packed": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_rasterize_backward_ordered": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_pack_records": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_rasterize_forward_packed_ex": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint, _vp]),
+    "gsb_rasterize_backward_ex": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint, _vp]),
     "gsb_rasterize_forward_count": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_activate_forward": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_activate_backward": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -117,6 +117,143 @@ torch::autograd::tensor_list SphericalHarmonicsRgb::backward(torch::autograd::Au
     return {torch::Tensor(), torch::Tensor(), torch::Tensor(), vDc, vRest};
 }
 
+torch::autograd::variable_list ProjectGaussiansActivated::forward(
+    torch::autograd::AutogradContext *ctx, torch::Tensor means, torch::Tensor logScales, double globScale,
+    torch::Tensor rawQuats, torch::Tensor opacityLogits, torch::Tensor viewMat, torch::Tensor projMat, double fx,
+    double fy, double cx, double cy, int64_t imgHeight, int64_t imgWidth, std::tuple<int, int, int> tileBounds,
+    double clipThresh) {
+    const int n = (int)means.size(0);
+    c10::cuda::CUDAGuard guard(means.device());
+    TORCH_CHECK(opacityLogits.numel() == n, "ProjectGaussiansActivated: opacityLogits must hold one value per Gaussian");
+    torch::Tensor m = f32(means), ls = f32(logScales), rq = f32(rawQuats), ol = f32(opacityLogits).reshape({-1});
+    torch::Tensor V = f32(viewMat), P = f32(projMat);
+    torch::Tensor cov3d = torch::empty({n, 6}, like(m, torch::kFloat32));
+    torch::Tensor xys = torch::empty({n, 2}, like(m, torch::kFloat32));
+    torch::Tensor depths = torch::empty({n}, like(m, torch::kFloat32));
+    torch::Tensor radii = torch::empty({n}, like(m, torch::kInt32));
+    torch::Tensor conics = torch::empty({n, 3}, like(m, torch::kFloat32));
+    torch::Tensor numTilesHit = torch::empty({n}, like(m, torch::kInt32));
+    torch::Tensor opac = torch::empty({n, 1}, like(m, torch::kFloat32));
+    check(gsb_project_forward_activated(n, fp(m), fp(ls), (float)globScale, fp(rq), fp(ol), fp(V), fp(P), (float)fx,
+                                        (float)fy, (float)cx, (float)cy, (int)imgHeight, (int)imgWidth,
+                                        std::get<0>(tileBounds), std::get<1>(tileBounds), (float)clipThresh,
+                                        fpw(cov3d), fpw(xys), fpw(depths), radii.data_ptr<int32_t>(), fpw(conics),
+                                        numTilesHit.data_ptr<int32_t>(), fpw(opac), stream()),
+          "gsb_project_forward_activated");
+    ctx->saved_data["imgHeight"] = imgHeight;
+    ctx->saved_data["imgWidth"] = imgWidth;
+    ctx->saved_data["globScale"] = globScale;
+    ctx->saved_data["fx"] = fx;
+    ctx->saved_data["fy"] = fy;
+    ctx->saved_data["logitSizes"] = opacityLogits.sizes().vec();
+    ctx->save_for_backward({m, ls, rq, V, P, radii, conics, opac});
+    ctx->mark_non_differentiable({radii, numTilesHit});
+    return {xys, depths, radii, conics, numTilesHit, cov3d, opac};
+}
+
+torch::autograd::tensor_list ProjectGaussiansActivated::backward(torch::autograd::AutogradContext *ctx,
+                                                                 torch::autograd::tensor_list g) {
+    auto saved = ctx->get_saved_variables();
+    torch::Tensor m = saved[0], ls = saved[1], rq = saved[2], V = saved[3], P = saved[4];
+    torch::Tensor radii = saved[5], conics = saved[6], opac = saved[7];
+    const int n = (int)m.size(0);
+    c10::cuda::CUDAGuard guard(m.device());
+    // cotangents of xys (0), depths (1), conics (3), opacities (6); undefined == zeros
+    torch::Tensor v_xy = g[0].defined() ? f32(g[0]) : torch::zeros({n, 2}, like(m, torch::kFloat32));
+    torch::Tensor v_depth = g[1].defined() ? f32(g[1]) : torch::Tensor();
+    torch::Tensor v_conic = g[3].defined() ? f32(g[3]) : torch::zeros({n, 3}, like(m, torch::kFloat32));
+    torch::Tensor v_opac = g[6].defined() ? f32(g[6]) : torch::Tensor();
+    torch::Tensor v_mean = torch::empty({n, 3}, like(m, torch::kFloat32));
+    torch::Tensor v_ls = torch::empty({n, 3}, like(m, torch::kFloat32));
+    torch::Tensor v_rq = torch::empty({n, 4}, like(m, torch::kFloat32));
+    torch::Tensor v_ol = torch::empty({n}, like(m, torch::kFloat32));
+    check(gsb_project_backward_activated(
+              n, fp(m), fp(ls), (float)ctx->saved_data["globScale"].toDouble(), fp(rq), fp(opac), fp(V), fp(P),
+              (float)ctx->saved_data["fx"].toDouble(), (float)ctx->saved_data["fy"].toDouble(),
+              (int)ctx->saved_data["imgHeight"].toInt(), (int)ctx->saved_data["imgWidth"].toInt(),
+              radii.data_ptr<int32_t>(), fp(conics), fp(v_xy), v_depth.defined() ? fp(v_depth) : nullptr, fp(v_conic),
+              v_opac.defined() ? fp(v_opac) : nullptr, fpw(v_mean), fpw(v_ls), fpw(v_rq), fpw(v_ol), stream()),
+          "gsb_project_backward_activated");
+    torch::Tensor none;
+    return {v_mean, v_ls, none, v_rq, v_ol.reshape(ctx->saved_data["logitSizes"].toIntVector()),
+            none, none, none, none, none, none, none, none, none, none};
+}
+
+torch::Tensor RasterizeGaussiansClamped::forward(torch::autograd::AutogradContext *ctx, torch::Tensor xys,
+                                                 torch::Tensor depths, torch::Tensor radii, torch::Tensor conics,
+                                                 torch::Tensor numTilesHit, torch::Tensor colors,
+                                                 torch::Tensor opacity, int imgHeight, int imgWidth,
+                                                 torch::Tensor background) {
+    return rasterizeForward(ctx, GSB_RASTER_CLAMP_MAX_ONE, xys, depths, radii, conics, numTilesHit, colors, opacity,
+                            imgHeight, imgWidth, background);
+}
+
+torch::autograd::tensor_list RasterizeGaussiansClamped::backward(torch::autograd::AutogradContext *ctx,
+                                                                 torch::autograd::tensor_list grad_outputs) {
+    return rasterizeBackward(ctx, grad_outputs);
+}
+
+ModelForwardResult modelForward(const torch::Tensor &means, const torch::Tensor &logScales,
+                                const torch::Tensor &rawQuats, const torch::Tensor &featuresDc,
+                                const torch::Tensor &featuresRest, const torch::Tensor &opacityLogits,
+                                const torch::Tensor &backgroundColor, const torch::Tensor &camToWorld, float fx,
+                                float fy, float cx, float cy, int height, int width, int degreesToUse) {
+    TORCH_CHECK(camToWorld.dim() == 2 && camToWorld.size(0) >= 3 && camToWorld.size(1) == 4,
+                "modelForward: camToWorld must be [3|4, 4]");
+    c10::cuda::CUDAGuard guard(means.device());
+    // host side of model.cpp:92-113: R = c2w[:3,:3] diag(1,-1,-1) (gsplat's axis convention), worldToCam = [R^T | -R^T T],
+    // OpenGL-style projection from the fields of view, projMat @ viewMat; plus the camera centre for the SH pass
+    torch::Tensor c2w = camToWorld.to(torch::kCPU, torch::kFloat32).contiguous();
+    auto a = c2w.accessor<float, 2>();
+    const float flip[3] = {1.f, -1.f, -1.f};
+    float V[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 1}};
+    for (int i = 0; i < 3; ++i) {
+        float t = 0.f;
+        for (int j = 0; j < 3; ++j) {
+            V[i][j] = a[j][i] * flip[i];                  // (R^T)[i][j] = R[j][i] = c2w[j][i] * flip[i]
+            t += -V[i][j] * a[j][3];
+        }
+        V[i][3] = t;
+    }
+    const float zNear = 0.001f, zFar = 1000.0f;
+    const float fovX = 2.0f * std::atan(width / (2.0f * fx)), fovY = 2.0f * std::atan(height / (2.0f * fy));
+    const float top = zNear * std::tan(0.5f * fovY), right = zNear * std::tan(0.5f * fovX);
+    const float P[4][4] = {{2.0f * zNear / (2.0f * right), 0.f, 0.f, 0.f},
+                           {0.f, 2.0f * zNear / (2.0f * top), 0.f, 0.f},
+                           {0.f, 0.f, (zFar + zNear) / (zFar - zNear), -1.0f * zFar * zNear / (zFar - zNear)},
+                           {0.f, 0.f, 1.f, 0.f}};
+    torch::Tensor host = torch::empty({35}, torch::TensorOptions().dtype(torch::kFloat32));
+    float *h = host.data_ptr<float>();
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            h[4 * i + j] = V[i][j];
+            float acc = 0.f;
+            for (int k = 0; k < 4; ++k) acc += P[i][k] * V[k][j];
+            h[16 + 4 * i + j] = acc;
+        }
+    for (int i = 0; i < 3; ++i) h[32 + i] = a[i][3];
+    torch::Tensor devBuf = host.to(means.device());
+    torch::Tensor viewMat = devBuf.slice(0, 0, 16).view({4, 4}), fullProj = devBuf.slice(0, 16, 32).view({4, 4});
+    torch::Tensor camPos = devBuf.slice(0, 32, 35);
+
+    const std::tuple<int, int, int> tileBounds = std::make_tuple((width + 15) / 16, (height + 15) / 16, 1);
+    auto p = ProjectGaussiansActivated::apply(means, logScales, 1.0, rawQuats, opacityLogits, viewMat, fullProj,
+                                              (double)fx, (double)fy, (double)cx, (double)cy, (int64_t)height,
+                                              (int64_t)width, tileBounds, 0.01);
+    ModelForwardResult r;
+    r.xys = p[0];
+    r.radii = p[2];
+    r.xys.retain_grad();
+    if (r.radii.sum().item<float>() == 0.0f) {       // model.cpp:173-174
+        r.rgb = backgroundColor.repeat({height, width, 1});
+        return r;
+    }
+    torch::Tensor rgbs = SphericalHarmonicsRgb::apply((int64_t)degreesToUse, means.detach(), camPos, featuresDc,
+                                                      featuresRest);
+    r.rgb = RasterizeGaussiansClamped::apply(p[0], p[1], p[2], p[3], p[4], rgbs, p[6], height, width, backgroundColor);
+    return r;
+}
+
 void adamStep(torch::Tensor param, const torch::Tensor &grad, torch::Tensor expAvg, torch::Tensor expAvgSq, double lr,
               int64_t step, double beta1, double beta2, double eps) {
     TORCH_CHECK(param.is_cuda() && param.is_contiguous() && param.scalar_type() == torch::kFloat32,

@@ -7,6 +7,7 @@
 // and the six `xxxOpt->step()` calls (model.cpp:236-243) for gsb::adamStep on each parameter.
 #pragma once
 #include <torch/torch.h>
+#include <tuple>
 
 namespace gsb {
 
@@ -45,6 +46,55 @@ public:
     static torch::autograd::tensor_list backward(torch::autograd::AutogradContext *ctx,
                                                  torch::autograd::tensor_list grad_outputs);
 };
+
+// ProjectGaussians on the model's RAW parameters -- model.cpp:148-150 (`exp(scales)`, `quats / quats.norm()`),
+// model.cpp:200 (`sigmoid(opacities)`) and model.cpp:152-165 as one operator; the activations run as the projection
+// kernels' prologue / epilogue, gradients come back w.r.t. the raw parameters:
+//   auto p = gsb::ProjectGaussiansActivated::apply(means, scales, 1, quats, opacities, viewMat, projMat @ viewMat,
+//                                                  fx, fy, cx, cy, height, width, tileBounds);
+//   // p[0..5] = xys, depths, radii, conics, numTilesHit, cov3d (as ProjectGaussians), p[6] = sigmoid(opacities) [N,1]
+class ProjectGaussiansActivated : public torch::autograd::Function<ProjectGaussiansActivated> {
+public:
+    static torch::autograd::variable_list forward(torch::autograd::AutogradContext *ctx, torch::Tensor means,
+                                                  torch::Tensor logScales, double globScale, torch::Tensor rawQuats,
+                                                  torch::Tensor opacityLogits, torch::Tensor viewMat,
+                                                  torch::Tensor projMat, double fx, double fy, double cx, double cy,
+                                                  int64_t imgHeight, int64_t imgWidth,
+                                                  std::tuple<int, int, int> tileBounds, double clipThresh = 0.01);
+    static torch::autograd::tensor_list backward(torch::autograd::AutogradContext *ctx,
+                                                 torch::autograd::tensor_list grad_outputs);
+};
+
+// `rgb = RasterizeGaussians::apply(...); rgb = torch::clamp_max(rgb, 1.0f);` (model.cpp:213-222) as one operator:
+// the blend kernel writes the clamped image, the backward blend kernel applies clamp_max's gradient mask.
+// Same arguments and gradient slots as RasterizeGaussians.
+class RasterizeGaussiansClamped : public torch::autograd::Function<RasterizeGaussiansClamped> {
+public:
+    static torch::Tensor forward(torch::autograd::AutogradContext *ctx, torch::Tensor xys, torch::Tensor depths,
+                                 torch::Tensor radii, torch::Tensor conics, torch::Tensor numTilesHit,
+                                 torch::Tensor colors, torch::Tensor opacity, int imgHeight, int imgWidth,
+                                 torch::Tensor background);
+    static torch::autograd::tensor_list backward(torch::autograd::AutogradContext *ctx,
+                                                 torch::autograd::tensor_list grad_outputs);
+};
+
+// Model::forward (model.cpp:82-225) with every glue op fused, on plain tensors -- what a maintainer calls from the
+// body of Model::forward to opt in:
+//     auto r = gsb::modelForward(means, scales, quats, featuresDc, featuresRest, opacities, backgroundColor,
+//                                cam.camToWorld, fx, fy, cx, cy, height, width, degreesToUse);
+//     xys = r.xys; radii = r.radii; lastHeight = height; lastWidth = width; return r.rgb;
+// = ProjectGaussiansActivated -> (nothing visible: background, as model.cpp:173-174) -> SphericalHarmonicsRgb ->
+// RasterizeGaussiansClamped; the camera matrices (model.cpp:92-113) are formed on the host and uploaded in one copy.
+// fx, fy, cx, cy, height, width are the already down-scaled values (model.cpp:84-90).  xys has retain_grad() set
+// (model.cpp:171) so that afterTrain finds xys.grad().
+struct ModelForwardResult {
+    torch::Tensor rgb, xys, radii;
+};
+ModelForwardResult modelForward(const torch::Tensor &means, const torch::Tensor &logScales,
+                                const torch::Tensor &rawQuats, const torch::Tensor &featuresDc,
+                                const torch::Tensor &featuresRest, const torch::Tensor &opacityLogits,
+                                const torch::Tensor &backgroundColor, const torch::Tensor &camToWorld, float fx,
+                                float fy, float cx, float cy, int height, int width, int degreesToUse);
 
 // One torch::optim::Adam step (no weight decay / amsgrad) on `param` in place with caller-held moments;
 // `step` is the 1-based step count of this parameter (AdamParamState::step after the increment).

@@ -29,4 +29,14 @@ inline torch::TensorOptions like(const torch::Tensor &t, torch::ScalarType dt) {
     return torch::TensorOptions().dtype(dt).device(t.device());
 }
 
+
+// Bodies of RasterizeGaussians::forward / backward with the GSB_RASTER_* flags of the blend kernels
+// (rasterize_gaussians.cpp); shared with gsb::RasterizeGaussiansClamped (fused_extras.cpp).
+torch::Tensor rasterizeForward(torch::autograd::AutogradContext *ctx, unsigned flags, torch::Tensor xys,
+                               torch::Tensor depths, torch::Tensor radii, torch::Tensor conics,
+                               torch::Tensor numTilesHit, torch::Tensor colors, torch::Tensor opacity, int imgHeight,
+                               int imgWidth, torch::Tensor background);
+torch::autograd::tensor_list rasterizeBackward(torch::autograd::AutogradContext *ctx,
+                                               torch::autograd::tensor_list grad_outputs);
+
 }  // namespace gsb

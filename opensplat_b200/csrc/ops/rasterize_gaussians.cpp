@@ -106,10 +106,14 @@ inline char *align256(torch::Tensor &t) {
 
 }  // namespace
 
-torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xys, torch::Tensor depths,
-                                          torch::Tensor radii, torch::Tensor conics, torch::Tensor numTilesHit,
-                                          torch::Tensor colors, torch::Tensor opacity, int imgHeight,
-                                          int imgWidth, torch::Tensor background) {
+namespace gsb {
+
+// Body of RasterizeGaussians::forward; `flags` = GSB_RASTER_* (gsb::RasterizeGaussiansClamped passes
+// GSB_RASTER_CLAMP_MAX_ONE: clamp_max(rgb, 1) fused into the blend kernels, fused_extras.hpp).
+torch::Tensor rasterizeForward(AutogradContext *ctx, unsigned flags, torch::Tensor xys, torch::Tensor depths,
+                               torch::Tensor radii, torch::Tensor conics, torch::Tensor numTilesHit,
+                               torch::Tensor colors, torch::Tensor opacity, int imgHeight, int imgWidth,
+                               torch::Tensor background) {
     const int n = (int)xys.size(0);
     TORCH_CHECK(colors.size(-1) == 3, "RasterizeGaussians: only 3 colour channels are supported");
     c10::cuda::CUDAGuard guard(xys.device());
@@ -155,11 +159,11 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
                                             tileBins.data_ptr<int32_t>(), stats.data_ptr<int32_t>(), wp, wsBytes,
                                             records.data_ptr(), nullptr, nullptr, gsb::stream()),
                        "gsb_bucket_sort_pack");
-        gsb::check(gsb_rasterize_forward_packed(imgHeight, imgWidth, tilesX, tilesY, mCap,
-                                                tileBins.data_ptr<int32_t>(), tileOrder.data_ptr<int32_t>(),
-                                                stats.data_ptr<int32_t>(), gsb::fp(bg),
-                                                records.data_ptr(), gsb::fpw(outImg), gsb::fpw(finalTs),
-                                                finalIdx.data_ptr<int32_t>(), gsb::stream()),
+        gsb::check(gsb_rasterize_forward_packed_ex(imgHeight, imgWidth, tilesX, tilesY, mCap,
+                                                   tileBins.data_ptr<int32_t>(), tileOrder.data_ptr<int32_t>(),
+                                                   stats.data_ptr<int32_t>(), gsb::fp(bg), records.data_ptr(),
+                                                   gsb::fpw(outImg), gsb::fpw(finalTs),
+                                                   finalIdx.data_ptr<int32_t>(), flags, gsb::stream()),
                    "gsb_rasterize_forward_packed");
         // the path's single device->host read-back (rasterize_gaussians.cpp:63), waited for with the GPU busy
         statsReady.synchronize();
@@ -183,12 +187,14 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
         Binned b = bin_and_sort(n, mRef, x, d, r, cum, tileBounds);
         tileBins = b.tileBins;
         records = torch::empty({(int64_t)gsb_raster_records_bytes(mRef)}, gsb::like(x, torch::kUInt8));
-        gsb::check(gsb_rasterize_forward(imgHeight, imgWidth, tilesX, tilesY, mRef,
-                                         b.gaussianIdsSorted.data_ptr<int32_t>(),
-                                         b.sortedIndex.data_ptr<int32_t>(), b.tileBins.data_ptr<int32_t>(),
-                                         gsb::fp(x), gsb::fp(con), gsb::fp(col), gsb::fp(op), gsb::fp(bg),
-                                         records.data_ptr(), gsb::fpw(outImg), gsb::fpw(finalTs),
-                                         finalIdx.data_ptr<int32_t>(), gsb::stream()),
+        gsb::check(gsb_pack_records(mRef, b.gaussianIdsSorted.data_ptr<int32_t>(), b.sortedIndex.data_ptr<int32_t>(),
+                                    gsb::fp(x), gsb::fp(con), gsb::fp(col), gsb::fp(op), records.data_ptr(),
+                                    gsb::stream()),
+                   "gsb_pack_records");
+        gsb::check(gsb_rasterize_forward_packed_ex(imgHeight, imgWidth, tilesX, tilesY, mRef,
+                                                   b.tileBins.data_ptr<int32_t>(), nullptr, nullptr, gsb::fp(bg),
+                                                   records.data_ptr(), gsb::fpw(outImg), gsb::fpw(finalTs),
+                                                   finalIdx.data_ptr<int32_t>(), flags, gsb::stream()),
                    "gsb_rasterize_forward");
         mRaster = mRef;
         ordered = false;
@@ -199,11 +205,13 @@ torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xy
     ctx->saved_data["imgHeight"] = imgHeight;
     ctx->saved_data["numIntersects"] = mRaster;
     ctx->saved_data["ordered"] = ordered;
+    ctx->saved_data["flags"] = (int64_t)flags;
     ctx->save_for_backward({tileBins, con, op, records, cum, bg, finalTs, finalIdx, tileOrder});
     return outImg;
 }
 
-tensor_list RasterizeGaussians::backward(AutogradContext *ctx, tensor_list grad_outputs) {
+tensor_list rasterizeBackward(AutogradContext *ctx, tensor_list grad_outputs) {
+    const unsigned flags = (unsigned)ctx->saved_data["flags"].toInt();
     const int imgHeight = (int)ctx->saved_data["imgHeight"].toInt();
     const int imgWidth = (int)ctx->saved_data["imgWidth"].toInt();
     const int m = (int)ctx->saved_data["numIntersects"].toInt();
@@ -220,16 +228,30 @@ tensor_list RasterizeGaussians::backward(AutogradContext *ctx, tensor_list grad_
     torch::Tensor v_colors = torch::empty({n, 3}, gsb::like(con, torch::kFloat32));
     torch::Tensor v_opacity = torch::empty({n, 1}, gsb::like(con, torch::kFloat32));
     // v_output_alpha is identically zero in the reference (rasterize_gaussians.cpp:108) -> NULL
-    gsb::check(gsb_rasterize_backward_ordered(imgHeight, imgWidth, (imgWidth + BLOCK_X - 1) / BLOCK_X,
-                                      (imgHeight + BLOCK_Y - 1) / BLOCK_Y, n, m, tileBins.data_ptr<int32_t>(),
-                                      ordered ? tileOrder.data_ptr<int32_t>() : nullptr,
-                                      gsb::fp(con), gsb::fp(op), records.data_ptr(), cum.data_ptr<int32_t>(),
-                                      gsb::fp(bg), gsb::fp(finalTs), finalIdx.data_ptr<int32_t>(), gsb::fp(v_out),
-                                      nullptr, rows.data_ptr(), gsb::fpw(v_xy), gsb::fpw(v_conic),
-                                      gsb::fpw(v_colors), gsb::fpw(v_opacity), gsb::stream()),
+    gsb::check(gsb_rasterize_backward_ex(imgHeight, imgWidth, (imgWidth + BLOCK_X - 1) / BLOCK_X,
+                                         (imgHeight + BLOCK_Y - 1) / BLOCK_Y, n, m, tileBins.data_ptr<int32_t>(),
+                                         ordered ? tileOrder.data_ptr<int32_t>() : nullptr, gsb::fp(con), gsb::fp(op),
+                                         records.data_ptr(), cum.data_ptr<int32_t>(), gsb::fp(bg), gsb::fp(finalTs),
+                                         finalIdx.data_ptr<int32_t>(), gsb::fp(v_out), nullptr, rows.data_ptr(),
+                                         gsb::fpw(v_xy), gsb::fpw(v_conic), gsb::fpw(v_colors), gsb::fpw(v_opacity),
+                                         flags, gsb::stream()),
                "gsb_rasterize_backward");
     torch::Tensor none;
     return {v_xy, none, none, v_conic, none, v_colors, v_opacity, none, none, none};
+}
+
+}  // namespace gsb
+
+torch::Tensor RasterizeGaussians::forward(AutogradContext *ctx, torch::Tensor xys, torch::Tensor depths,
+                                          torch::Tensor radii, torch::Tensor conics, torch::Tensor numTilesHit,
+                                          torch::Tensor colors, torch::Tensor opacity, int imgHeight,
+                                          int imgWidth, torch::Tensor background) {
+    return gsb::rasterizeForward(ctx, 0u, xys, depths, radii, conics, numTilesHit, colors, opacity, imgHeight,
+                                 imgWidth, background);
+}
+
+tensor_list RasterizeGaussians::backward(AutogradContext *ctx, tensor_list grad_outputs) {
+    return gsb::rasterizeBackward(ctx, grad_outputs);
 }
 
 torch::Tensor RasterizeGaussiansCPU::forward(AutogradContext *, torch::Tensor, torch::Tensor, torch::Tensor,

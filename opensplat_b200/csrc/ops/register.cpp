@@ -60,7 +60,27 @@ static torch::Tensor op_sh_rgb(int64_t degreesToUse, torch::Tensor means, torch:
     return gsb::SphericalHarmonicsRgb::apply(degreesToUse, means, camPos, featuresDc, featuresRest);
 }
 
+static std::vector<torch::Tensor> op_project_activated(torch::Tensor means, torch::Tensor logScales, double globScale,
+                                                       torch::Tensor rawQuats, torch::Tensor opacityLogits,
+                                                       torch::Tensor viewMat, torch::Tensor projMat, double fx,
+                                                       double fy, double cx, double cy, int64_t imgHeight,
+                                                       int64_t imgWidth, double clipThresh) {
+    TileBounds tb = std::make_tuple((int)(imgWidth + BLOCK_X - 1) / BLOCK_X, (int)(imgHeight + BLOCK_Y - 1) / BLOCK_Y, 1);
+    return gsb::ProjectGaussiansActivated::apply(means, logScales, globScale, rawQuats, opacityLogits, viewMat,
+                                                 projMat, fx, fy, cx, cy, imgHeight, imgWidth, tb, clipThresh);
+}
+
+static torch::Tensor op_rasterize_clamped(torch::Tensor xys, torch::Tensor depths, torch::Tensor radii,
+                                          torch::Tensor conics, torch::Tensor numTilesHit, torch::Tensor colors,
+                                          torch::Tensor opacity, int64_t imgHeight, int64_t imgWidth,
+                                          torch::Tensor background) {
+    return gsb::RasterizeGaussiansClamped::apply(xys, depths, radii, conics, numTilesHit, colors, opacity,
+                                                 (int)imgHeight, (int)imgWidth, background);
+}
+
 TORCH_LIBRARY(opensplat_b200, m) {
+    m.def("project_gaussians_activated", &op_project_activated);
+    m.def("rasterize_gaussians_clamped", &op_rasterize_clamped);
     m.def("activate_gaussians", &op_activate);
     m.def("spherical_harmonics_rgb", &op_sh_rgb);
     m.def("project_gaussians", &op_project);

@@ -48,6 +48,11 @@ __device__ __forceinline__ void load_cam(const float *__restrict__ viewmat,
     for (int i = 0; i < 16; ++i) c.P[i] = __ldg(projmat + i);
 }
 
+// ACT: the parameter activations of Model::forward (model.cpp:148-150,176-177,200) as this kernel's prologue --
+// `scales` holds log-scales (exp here), `quats` the raw quaternions (quat_to_rotmat normalises, as the reference's
+// does, so `quats / quats.norm()` needs no pass of its own), and sigmoid(opacity_logits) is written beside the
+// projection outputs for the rasterizer.
+template <bool ACT>
 __global__ void __launch_bounds__(PJ_THREADS)
 project_forward_kernel(int n, const float *__restrict__ means3d, const float *__restrict__ scales,
                        float glob_scale, const float *__restrict__ quats,
@@ -55,9 +60,11 @@ project_forward_kernel(int n, const float *__restrict__ means3d, const float *__
                        float fy, float cx, float cy, float tan_fovx, float tan_fovy, int img_h, int img_w,
                        int tiles_x, int tiles_y, float clip_thresh, float *__restrict__ cov3d,
                        float2 *__restrict__ xys, float *__restrict__ depths, int *__restrict__ radii,
-                       float *__restrict__ conics, int *__restrict__ num_tiles_hit) {
+                       float *__restrict__ conics, int *__restrict__ num_tiles_hit,
+                       const float *__restrict__ opacity_logits, float *__restrict__ opacities) {
     const int i = blockIdx.x * PJ_THREADS + threadIdx.x;
     if (i >= n) return;
+    if (ACT) opacities[i] = 1.f / (1.f + expf(-opacity_logits[i]));
     Cam cam;
     load_cam(viewmat, projmat, cam);
     const float *V = cam.V, *P = cam.P;
@@ -77,8 +84,9 @@ project_forward_kernel(int n, const float *__restrict__ means3d, const float *__
         const float4 q = reinterpret_cast<const float4 *>(quats)[i];  // (w,x,y,z)
         float R[3][3], M[3][3];
         quat_to_rotmat(q.x, q.y, q.z, q.w, R);
-        const float s0 = glob_scale * scales[3 * i], s1 = glob_scale * scales[3 * i + 1],
-                    s2 = glob_scale * scales[3 * i + 2];
+        const float a0 = scales[3 * i], a1 = scales[3 * i + 1], a2 = scales[3 * i + 2];
+        const float s0 = glob_scale * (ACT ? expf(a0) : a0), s1 = glob_scale * (ACT ? expf(a1) : a1),
+                    s2 = glob_scale * (ACT ? expf(a2) : a2);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             M[r][0] = R[r][0] * s0;
@@ -166,6 +174,10 @@ project_forward_kernel(int n, const float *__restrict__ means3d, const float *__
     num_tiles_hit[i] = area;
 }
 
+// ACT: VJP of the activating forward -- v_scale comes out w.r.t. the LOG-scales (x exp), the quaternion gradient
+// is w.r.t. the raw quaternion as always (the normalisation is inside quat_to_rotmat), and the rasterizer's opacity
+// gradient is taken through the sigmoid (x o (1 - o), from the saved activated opacity).
+template <bool ACT>
 __global__ void __launch_bounds__(PJ_THREADS)
 project_backward_kernel(int n, const float *__restrict__ means3d, const float *__restrict__ scales,
                         float glob_scale, const float *__restrict__ quats,
@@ -174,9 +186,15 @@ project_backward_kernel(int n, const float *__restrict__ means3d, const float *_
                         const int *__restrict__ radii, const float *__restrict__ conics,
                         const float2 *__restrict__ v_xy, const float *__restrict__ v_depth,
                         const float *__restrict__ v_conic, float *__restrict__ v_mean3d,
-                        float *__restrict__ v_scale, float4 *__restrict__ v_quat) {
+                        float *__restrict__ v_scale, float4 *__restrict__ v_quat,
+                        const float *__restrict__ opacities, const float *__restrict__ v_opacity,
+                        float *__restrict__ v_opacity_logits) {
     const int i = blockIdx.x * PJ_THREADS + threadIdx.x;
     if (i >= n) return;
+    if (ACT) {
+        const float o = opacities[i];
+        v_opacity_logits[i] = v_opacity ? v_opacity[i] * o * (1.f - o) : 0.f;
+    }
     float vm[3] = {0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
     float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
     if (radii[i] > 0) {
@@ -216,8 +234,9 @@ project_backward_kernel(int n, const float *__restrict__ means3d, const float *_
         const float4 q = reinterpret_cast<const float4 *>(quats)[i];
         float R[3][3], M[3][3];
         quat_to_rotmat(q.x, q.y, q.z, q.w, R);
-        const float s[3] = {glob_scale * scales[3 * i], glob_scale * scales[3 * i + 1],
-                            glob_scale * scales[3 * i + 2]};
+        const float a[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+        const float e[3] = {ACT ? expf(a[0]) : a[0], ACT ? expf(a[1]) : a[1], ACT ? expf(a[2]) : a[2]};
+        const float s[3] = {glob_scale * e[0], glob_scale * e[1], glob_scale * e[2]};
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -279,8 +298,10 @@ project_backward_kernel(int n, const float *__restrict__ means3d, const float *_
             for (int c = 0; c < 3; ++c)
                 vM[r][c] = 2.f * (vV[r][0] * M[0][c] + vV[r][1] * M[1][c] + vV[r][2] * M[2][c]);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
             vs[c] = glob_scale * (R[0][c] * vM[0][c] + R[1][c] * vM[1][c] + R[2][c] * vM[2][c]);
+            if (ACT) vs[c] = vs[c] * e[c];   // d exp(a) = exp(a)
+        }
         float vR[3][3];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -307,24 +328,74 @@ project_backward_kernel(int n, const float *__restrict__ means3d, const float *_
 
 }  // namespace
 
+static int project_forward_impl(bool act, int n, const float *means3d, const float *scales, float glob_scale,
+                                const float *quats, const float *opacity_logits, const float *viewmat,
+                                const float *projmat, float fx, float fy, float cx, float cy, int img_h, int img_w,
+                                int tiles_x, int tiles_y, float clip_thresh, float *cov3d, float *xys, float *depths,
+                                int32_t *radii, float *conics, int32_t *num_tiles_hit, float *opacities,
+                                gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && img_h > 0 && img_w > 0 && tiles_x > 0 && tiles_y > 0);
+    if (n == 0) return 0;
+    GSB_CHECK_ARG(means3d && scales && quats && viewmat && projmat && cov3d && xys && depths && radii &&
+                  conics && num_tiles_hit);
+    GSB_CHECK_ARG(!act || (opacity_logits && opacities));
+    GSB_CHECK_ARG(((uintptr_t)quats % 16) == 0 && ((uintptr_t)xys % 8) == 0);
+    // forward.cu:69-70 evaluates `0.5 * img_size.x / fx` in double and narrows
+    const float tan_fovx = (float)(0.5 * (double)img_w / (double)fx);
+    const float tan_fovy = (float)(0.5 * (double)img_h / (double)fy);
+#define GSB_PJ_F(A) project_forward_kernel<A><<<gsb_div_up(n, PJ_THREADS), PJ_THREADS, 0, (cudaStream_t)stream>>>( \
+        n, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, tan_fovx, tan_fovy, img_h, img_w,   \
+        tiles_x, tiles_y, clip_thresh, cov3d, reinterpret_cast<float2 *>(xys), depths, radii, conics, num_tiles_hit, \
+        opacity_logits, opacities)
+    if (act) GSB_PJ_F(true); else GSB_PJ_F(false);
+#undef GSB_PJ_F
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int gsb_project_forward(int n, const float *means3d, const float *scales, float glob_scale,
                                    const float *quats, const float *viewmat, const float *projmat,
                                    float fx, float fy, float cx, float cy, int img_h, int img_w,
                                    int tiles_x, int tiles_y, float clip_thresh, float *cov3d, float *xys,
                                    float *depths, int32_t *radii, float *conics, int32_t *num_tiles_hit,
                                    gsb_stream_t stream) {
-    GSB_CHECK_ARG(n >= 0 && img_h > 0 && img_w > 0 && tiles_x > 0 && tiles_y > 0);
+    return project_forward_impl(false, n, means3d, scales, glob_scale, quats, nullptr, viewmat, projmat, fx, fy, cx,
+                                cy, img_h, img_w, tiles_x, tiles_y, clip_thresh, cov3d, xys, depths, radii, conics,
+                                num_tiles_hit, nullptr, stream);
+}
+
+extern "C" int gsb_project_forward_activated(int n, const float *means3d, const float *log_scales, float glob_scale,
+                                             const float *raw_quats, const float *opacity_logits,
+                                             const float *viewmat, const float *projmat, float fx, float fy,
+                                             float cx, float cy, int img_h, int img_w, int tiles_x, int tiles_y,
+                                             float clip_thresh, float *cov3d, float *xys, float *depths,
+                                             int32_t *radii, float *conics, int32_t *num_tiles_hit,
+                                             float *opacities, gsb_stream_t stream) {
+    return project_forward_impl(true, n, means3d, log_scales, glob_scale, raw_quats, opacity_logits, viewmat, projmat,
+                                fx, fy, cx, cy, img_h, img_w, tiles_x, tiles_y, clip_thresh, cov3d, xys, depths, radii,
+                                conics, num_tiles_hit, opacities, stream);
+}
+
+static int project_backward_impl(bool act, int n, const float *means3d, const float *scales, float glob_scale,
+                                 const float *quats, const float *opacities, const float *viewmat,
+                                 const float *projmat, float fx, float fy, int img_h, int img_w,
+                                 const int32_t *radii, const float *conics, const float *v_xy, const float *v_depth,
+                                 const float *v_conic, const float *v_opacity, float *v_mean3d, float *v_scale,
+                                 float *v_quat, float *v_opacity_logits, gsb_stream_t stream) {
+    GSB_CHECK_ARG(n >= 0 && img_h > 0 && img_w > 0);
     if (n == 0) return 0;
-    GSB_CHECK_ARG(means3d && scales && quats && viewmat && projmat && cov3d && xys && depths && radii &&
-                  conics && num_tiles_hit);
-    GSB_CHECK_ARG(((uintptr_t)quats % 16) == 0 && ((uintptr_t)xys % 8) == 0);
-    // forward.cu:69-70 evaluates `0.5 * img_size.x / fx` in double and narrows
+    GSB_CHECK_ARG(means3d && scales && quats && viewmat && projmat && radii && conics && v_xy && v_conic &&
+                  v_mean3d && v_scale && v_quat);
+    GSB_CHECK_ARG(!act || (opacities && v_opacity_logits));
+    GSB_CHECK_ARG(((uintptr_t)quats % 16) == 0 && ((uintptr_t)v_quat % 16) == 0 && ((uintptr_t)v_xy % 8) == 0);
     const float tan_fovx = (float)(0.5 * (double)img_w / (double)fx);
     const float tan_fovy = (float)(0.5 * (double)img_h / (double)fy);
-    project_forward_kernel<<<gsb_div_up(n, PJ_THREADS), PJ_THREADS, 0, (cudaStream_t)stream>>>(
-        n, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, tan_fovx, tan_fovy, img_h,
-        img_w, tiles_x, tiles_y, clip_thresh, cov3d, reinterpret_cast<float2 *>(xys), depths, radii, conics,
-        num_tiles_hit);
+#define GSB_PJ_B(A) project_backward_kernel<A><<<gsb_div_up(n, PJ_THREADS), PJ_THREADS, 0, (cudaStream_t)stream>>>( \
+        n, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, tan_fovx, tan_fovy, img_h, img_w, radii,     \
+        conics, reinterpret_cast<const float2 *>(v_xy), v_depth, v_conic, v_mean3d, v_scale,                          \
+        reinterpret_cast<float4 *>(v_quat), opacities, v_opacity, v_opacity_logits)
+    if (act) GSB_PJ_B(true); else GSB_PJ_B(false);
+#undef GSB_PJ_B
     GSB_LAUNCH_CHECK();
     return 0;
 }
@@ -336,17 +407,19 @@ extern "C" int gsb_project_backward(int n, const float *means3d, const float *sc
                                     const float *v_xy, const float *v_depth, const float *v_conic,
                                     float *v_mean3d, float *v_scale, float *v_quat, gsb_stream_t stream) {
     (void)cov3d; (void)cx; (void)cy;
-    GSB_CHECK_ARG(n >= 0 && img_h > 0 && img_w > 0);
-    if (n == 0) return 0;
-    GSB_CHECK_ARG(means3d && scales && quats && viewmat && projmat && radii && conics && v_xy && v_conic &&
-                  v_mean3d && v_scale && v_quat);
-    GSB_CHECK_ARG(((uintptr_t)quats % 16) == 0 && ((uintptr_t)v_quat % 16) == 0 && ((uintptr_t)v_xy % 8) == 0);
-    const float tan_fovx = (float)(0.5 * (double)img_w / (double)fx);
-    const float tan_fovy = (float)(0.5 * (double)img_h / (double)fy);
-    project_backward_kernel<<<gsb_div_up(n, PJ_THREADS), PJ_THREADS, 0, (cudaStream_t)stream>>>(
-        n, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, tan_fovx, tan_fovy, img_h, img_w,
-        radii, conics, reinterpret_cast<const float2 *>(v_xy), v_depth, v_conic, v_mean3d, v_scale,
-        reinterpret_cast<float4 *>(v_quat));
-    GSB_LAUNCH_CHECK();
-    return 0;
+    return project_backward_impl(false, n, means3d, scales, glob_scale, quats, nullptr, viewmat, projmat, fx, fy,
+                                 img_h, img_w, radii, conics, v_xy, v_depth, v_conic, nullptr, v_mean3d, v_scale,
+                                 v_quat, nullptr, stream);
+}
+
+extern "C" int gsb_project_backward_activated(int n, const float *means3d, const float *log_scales, float glob_scale,
+                                              const float *raw_quats, const float *opacities, const float *viewmat,
+                                              const float *projmat, float fx, float fy, int img_h, int img_w,
+                                              const int32_t *radii, const float *conics, const float *v_xy,
+                                              const float *v_depth, const float *v_conic, const float *v_opacity,
+                                              float *v_mean3d, float *v_log_scales, float *v_raw_quats,
+                                              float *v_opacity_logits, gsb_stream_t stream) {
+    return project_backward_impl(true, n, means3d, log_scales, glob_scale, raw_quats, opacities, viewmat, projmat, fx,
+                                 fy, img_h, img_w, radii, conics, v_xy, v_depth, v_conic, v_opacity, v_mean3d,
+                                 v_log_scales, v_raw_quats, v_opacity_logits, stream);
 }

@@ -45,6 +45,9 @@ __device__ __forceinline__ void zero_row(float *grad_rows, int k) {
 #ifndef GSB_BWD_MINB
 #define GSB_BWD_MINB 6   // 80 registers -> 6 CTAs per SM (measured)
 #endif
+// SAT: v_output is the gradient w.r.t. the CLAMPED image of the forward kernel's SAT instantiation -- channels
+// marked as cut in final_idx bits 28..30 receive no gradient (clamp_max's mask, model.cpp:222).
+template <bool SAT>
 __global__ void __launch_bounds__(RK_THREADS, GSB_BWD_MINB)
 rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                           const int2 *__restrict__ tile_bins, const GsbRecord *__restrict__ records,
@@ -95,10 +98,17 @@ rasterize_backward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 const float Tf = final_Ts[p];
                 T[j] = Tf;
                 vor[j] = v_output[3 * p]; vog[j] = v_output[3 * p + 1]; vob[j] = v_output[3 * p + 2];
+                binf[j] = final_idx[p];
+                if (SAT) {
+                    const int f = binf[j];
+                    if (f & GSB_SAT_BIT0) vor[j] = 0.f;
+                    if (f & (GSB_SAT_BIT0 << 1)) vog[j] = 0.f;
+                    if (f & (GSB_SAT_BIT0 << 2)) vob[j] = 0.f;
+                    binf[j] = f & ~GSB_SAT_MASK;
+                }
                 const float voa = v_output_alpha ? v_output_alpha[p] : 0.f;
                 // backward.cu:313-317: T_final*ra*v_out_alpha - T_final*ra*(bg . v_out)  ==  ra * q
                 Bq[j] = -(Tf * (voa - (bg0 * vor[j] + bg1 * vog[j] + bg2 * vob[j])));
-                binf[j] = final_idx[p];
             } else {
                 T[j] = 1.f; vor[j] = vog[j] = vob[j] = 0.f; Bq[j] = 0.f;
                 binf[j] = -1;  // never valid
@@ -307,8 +317,10 @@ static int rasterize_backward_impl(int img_h, int img_w, int tiles_x, int tiles_
                                    const float *final_Ts, const int32_t *final_idx,
                                    const float *v_output, const float *v_output_alpha,
                                    void *grad_rows, float *v_xy, float *v_conic, float *v_colors,
-                                   float *v_opacity, gsb_stream_t stream) {
+                                   float *v_opacity, unsigned flags, gsb_stream_t stream) {
     GSB_CHECK_ARG(img_h > 0 && img_w > 0 && n >= 0 && m >= 0);
+    GSB_CHECK_ARG((flags & ~(unsigned)GSB_RASTER_CLAMP_MAX_ONE) == 0);
+    const bool sat = (flags & GSB_RASTER_CLAMP_MAX_ONE) != 0;
     GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
     if (n == 0) return 0;
     GSB_CHECK_ARG(tile_bins && conics && opacities && cum_tiles_hit && background && final_Ts && final_idx &&
@@ -321,11 +333,14 @@ static int rasterize_backward_impl(int img_h, int img_w, int tiles_x, int tiles_
             reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
         GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
         const int num_tiles = tiles_x * tiles_y;
-        const int grid = gsb_blend_grid((const void *)rasterize_backward_kernel, num_tiles);
-        rasterize_backward_kernel<<<grid, RK_THREADS, 0, s>>>(
-            img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-            reinterpret_cast<const GsbRecord *>(records), background, final_Ts, final_idx, v_output,
-            v_output_alpha, reinterpret_cast<float *>(grad_rows), counters, tile_order);
+#define GSB_BWD_LAUNCH(S)                                                                                       \
+    rasterize_backward_kernel<S><<<gsb_blend_grid((const void *)rasterize_backward_kernel<S>, num_tiles),        \
+                                   RK_THREADS, 0, s>>>(                                                         \
+        img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),                            \
+        reinterpret_cast<const GsbRecord *>(records), background, final_Ts, final_idx, v_output, v_output_alpha, \
+        reinterpret_cast<float *>(grad_rows), counters, tile_order)
+        if (sat) GSB_BWD_LAUNCH(true); else GSB_BWD_LAUNCH(false);
+#undef GSB_BWD_LAUNCH
     }
     reduce_grad_rows_kernel<<<gsb_div_up(n, 256), 256, 0, s>>>(
         n, cum_tiles_hit, reinterpret_cast<const float *>(grad_rows), conics, opacities,
@@ -344,7 +359,7 @@ extern "C" int gsb_rasterize_backward(int img_h, int img_w, int tiles_x, int til
                                       float *v_opacity, gsb_stream_t stream) {
     return rasterize_backward_impl(img_h, img_w, tiles_x, tiles_y, n, m, tile_bins, nullptr, conics, opacities, records,
                                    cum_tiles_hit, background, final_Ts, final_idx, v_output, v_output_alpha, grad_rows,
-                                   v_xy, v_conic, v_colors, v_opacity, stream);
+                                   v_xy, v_conic, v_colors, v_opacity, 0u, stream);
 }
 
 // Same, with the tile order of gsb_bucket_tile_ranges (tiles handed to the persistent warps longest list first).
@@ -358,5 +373,20 @@ extern "C" int gsb_rasterize_backward_ordered(int img_h, int img_w, int tiles_x,
                                               float *v_opacity, gsb_stream_t stream) {
     return rasterize_backward_impl(img_h, img_w, tiles_x, tiles_y, n, m, tile_bins, tile_order, conics, opacities,
                                    records, cum_tiles_hit, background, final_Ts, final_idx, v_output, v_output_alpha,
-                                   grad_rows, v_xy, v_conic, v_colors, v_opacity, stream);
+                                   grad_rows, v_xy, v_conic, v_colors, v_opacity, 0u, stream);
+}
+
+// gsb_rasterize_backward_ordered with `flags`: GSB_RASTER_CLAMP_MAX_ONE = final_idx carries the cut mask written by
+// gsb_rasterize_forward_packed_ex under the same flag and v_output is the gradient of the clamped image.
+extern "C" int gsb_rasterize_backward_ex(int img_h, int img_w, int tiles_x, int tiles_y, int n, int m,
+                                         const int32_t *tile_bins, const int32_t *tile_order,
+                                         const float *conics, const float *opacities, void *records,
+                                         const int32_t *cum_tiles_hit, const float *background,
+                                         const float *final_Ts, const int32_t *final_idx,
+                                         const float *v_output, const float *v_output_alpha,
+                                         void *grad_rows, float *v_xy, float *v_conic, float *v_colors,
+                                         float *v_opacity, unsigned flags, gsb_stream_t stream) {
+    return rasterize_backward_impl(img_h, img_w, tiles_x, tiles_y, n, m, tile_bins, tile_order, conics, opacities,
+                                   records, cum_tiles_hit, background, final_Ts, final_idx, v_output, v_output_alpha,
+                                   grad_rows, v_xy, v_conic, v_colors, v_opacity, flags, stream);
 }

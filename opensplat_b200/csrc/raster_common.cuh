@@ -45,6 +45,11 @@ constexpr float GSB_SMAX_BIAS = 5.541263545158426f + 1e-3f;
 // The (linear) map to v_xy / v_conic / v_opacity is applied once per Gaussian by the row-reduce kernel.
 constexpr int GSB_GRAD_ROW_FLOATS = 12;
 
+// GSB_RASTER_CLAMP_MAX_ONE (gsplat_b200.h): the forward kernel's SAT instantiation marks the colour channels of a
+// pixel it cut at 1 in these bits of final_idx; the backward kernel's SAT instantiation strips them again.
+constexpr int GSB_SAT_BIT0 = 1 << 28;
+constexpr int GSB_SAT_MASK = 7 << 28;
+
 struct __align__(128) WarpRing {
     GsbRecord rec[RK_STAGES][RK_CHUNK];
     uint64_t full[RK_STAGES];

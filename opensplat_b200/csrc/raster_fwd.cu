@@ -55,7 +55,10 @@ pack_records_kernel(int m, const int *__restrict__ gaussian_ids_sorted,
 // totals of {records that pass the per-record test, slot visits, pixel pairs whose sigma is inside the
 // extent (ex2 evaluated), pixel pairs blended} in pair_counts[0..3].  The production instantiation carries none
 // of it.
-template <bool COUNT>
+// SAT = true fuses the caller's `clamp_max(rgb, 1)` (model.cpp:222) into the epilogue: the image is written clamped
+// and, per pixel, which channels were cut (!(value <= 1), torch's clamp_max mask) goes into bits 28..30 of final_idx
+// for the SAT instantiation of the backward kernel (sorted indices stay below 2^28, checked by the entry point).
+template <bool COUNT, bool SAT>
 __global__ void __launch_bounds__(RK_THREADS, GSB_FWD_MINB)
 rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                          const int2 *__restrict__ tile_bins, const GsbRecord *__restrict__ records,
@@ -221,10 +224,17 @@ rasterize_forward_kernel(int img_h, int img_w, int tiles_x, int num_tiles,
                 const size_t p = (size_t)Y * img_w + X;
                 const float Tf = fabsf(T[j]);
                 final_Ts[p] = Tf;
-                final_idx[p] = last[j];
-                out_img[3 * p] = cr[j] + Tf * bg0;
-                out_img[3 * p + 1] = cg[j] + Tf * bg1;
-                out_img[3 * p + 2] = cb[j] + Tf * bg2;
+                float o0 = cr[j] + Tf * bg0, o1 = cg[j] + Tf * bg1, o2 = cb[j] + Tf * bg2;
+                int fi = last[j];
+                if (SAT) {
+                    if (!(o0 <= 1.f)) { fi |= GSB_SAT_BIT0; o0 = o0 > 1.f ? 1.f : o0; }
+                    if (!(o1 <= 1.f)) { fi |= GSB_SAT_BIT0 << 1; o1 = o1 > 1.f ? 1.f : o1; }
+                    if (!(o2 <= 1.f)) { fi |= GSB_SAT_BIT0 << 2; o2 = o2 > 1.f ? 1.f : o2; }
+                }
+                final_idx[p] = fi;
+                out_img[3 * p] = o0;
+                out_img[3 * p + 1] = o1;
+                out_img[3 * p + 2] = o2;
             }
         }
     }
@@ -252,35 +262,61 @@ extern "C" size_t gsb_raster_records_bytes(int m) {
     return gsb_align_up((size_t)(m > 0 ? m : 0) * sizeof(GsbRecord), 256) + 256;
 }
 
+// records <- the per-intersection 48-byte blend records of a sorted intersection list (generic binning path)
+extern "C" int gsb_pack_records(int m, const int32_t *gaussian_ids_sorted, const int32_t *sorted_index,
+                                const float *xys, const float *conics, const float *colors, const float *opacities,
+                                void *records, gsb_stream_t stream) {
+    GSB_CHECK_ARG(m >= 0);
+    if (m == 0) return 0;
+    GSB_CHECK_ARG(records && gaussian_ids_sorted && xys && conics && colors && opacities);
+    GSB_CHECK_ARG(((uintptr_t)records % 16) == 0 && ((uintptr_t)xys % 8) == 0);
+    pack_records_kernel<<<gsb_div_up(m, 256), 256, 0, (cudaStream_t)stream>>>(
+        m, gaussian_ids_sorted, sorted_index, reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
+        reinterpret_cast<GsbRecord *>(records));
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int blend_forward(int img_h, int img_w, int tiles_x, int tiles_y, int m, const int32_t *tile_bins,
+                         const int32_t *tile_order, const int32_t *bin_stats, const float *background,
+                         void *records, float *out_img, float *final_Ts, int32_t *final_idx, unsigned flags,
+                         gsb_stream_t stream) {
+    GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0);
+    GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
+    GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx && records);
+    GSB_CHECK_ARG(((uintptr_t)records % 16) == 0);
+    GSB_CHECK_ARG((flags & ~(unsigned)GSB_RASTER_CLAMP_MAX_ONE) == 0);
+    const bool sat = (flags & GSB_RASTER_CLAMP_MAX_ONE) != 0;
+    GSB_CHECK_ARG(!sat || m < GSB_SAT_BIT0);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned *counters = reinterpret_cast<unsigned *>(
+        reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
+    GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
+    const int num_tiles = tiles_x * tiles_y;
+#define GSB_FWD_LAUNCH(S)                                                                                        \
+    rasterize_forward_kernel<false, S><<<gsb_blend_grid((const void *)rasterize_forward_kernel<false, S>, num_tiles), \
+                                         RK_THREADS, 0, s>>>(                                                    \
+        img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),                             \
+        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters,        \
+        bin_stats, nullptr, tile_order)
+    if (sat) GSB_FWD_LAUNCH(true); else GSB_FWD_LAUNCH(false);
+#undef GSB_FWD_LAUNCH
+    GSB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int gsb_rasterize_forward(int img_h, int img_w, int tiles_x, int tiles_y, int m,
                                      const int32_t *gaussian_ids_sorted, const int32_t *sorted_index,
                                      const int32_t *tile_bins, const float *xys, const float *conics,
                                      const float *colors, const float *opacities,
                                      const float *background, void *records, float *out_img,
                                      float *final_Ts, int32_t *final_idx, gsb_stream_t stream) {
-    GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0);
-    GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
-    GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx && records);
-    GSB_CHECK_ARG(((uintptr_t)records % 16) == 0);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (m > 0) {
-        GSB_CHECK_ARG(gaussian_ids_sorted && xys && conics && colors && opacities);
-        GSB_CHECK_ARG(((uintptr_t)xys % 8) == 0);
-        pack_records_kernel<<<gsb_div_up(m, 256), 256, 0, s>>>(
-            m, gaussian_ids_sorted, sorted_index, reinterpret_cast<const float2 *>(xys), conics, colors,
-            opacities, reinterpret_cast<GsbRecord *>(records));
-    }
-    unsigned *counters = reinterpret_cast<unsigned *>(
-        reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
-    GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
-    const int num_tiles = tiles_x * tiles_y;
-    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel<false>, num_tiles);
-    rasterize_forward_kernel<false><<<grid, RK_THREADS, 0, s>>>(
-        img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr,
-        nullptr, nullptr);
-    GSB_LAUNCH_CHECK();
-    return 0;
+    GSB_CHECK_ARG(m >= 0 && records);
+    const int rc = gsb_pack_records(m, gaussian_ids_sorted, sorted_index, xys, conics, colors, opacities, records,
+                                    stream);
+    if (rc) return rc;
+    return blend_forward(img_h, img_w, tiles_x, tiles_y, m, tile_bins, nullptr, nullptr, background, records, out_img,
+                         final_Ts, final_idx, 0u, stream);
 }
 
 extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, int tiles_y, int m,
@@ -288,22 +324,19 @@ extern "C" int gsb_rasterize_forward_packed(int img_h, int img_w, int tiles_x, i
                                             const int32_t *bin_stats, const float *background, void *records,
                                             float *out_img,
                                             float *final_Ts, int32_t *final_idx, gsb_stream_t stream) {
-    GSB_CHECK_ARG(img_h > 0 && img_w > 0 && m >= 0);
-    GSB_CHECK_ARG(tiles_x == gsb_div_up(img_w, GSB_TILE) && tiles_y == gsb_div_up(img_h, GSB_TILE));
-    GSB_CHECK_ARG(tile_bins && background && out_img && final_Ts && final_idx && records);
-    GSB_CHECK_ARG(((uintptr_t)records % 16) == 0);
-    cudaStream_t s = (cudaStream_t)stream;
-    unsigned *counters = reinterpret_cast<unsigned *>(
-        reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
-    GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
-    const int num_tiles = tiles_x * tiles_y;
-    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel<false>, num_tiles);
-    rasterize_forward_kernel<false><<<grid, RK_THREADS, 0, s>>>(
-        img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
-        reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, bin_stats,
-        nullptr, tile_order);
-    GSB_LAUNCH_CHECK();
-    return 0;
+    return blend_forward(img_h, img_w, tiles_x, tiles_y, m, tile_bins, tile_order, bin_stats, background, records,
+                         out_img, final_Ts, final_idx, 0u, stream);
+}
+
+// gsb_rasterize_forward_packed with `flags` (GSB_RASTER_*): GSB_RASTER_CLAMP_MAX_ONE writes min(out, 1) and keeps
+// the per-channel cut mask in final_idx bits 28..30 (to be handed to gsb_rasterize_backward_ex with the same flag).
+extern "C" int gsb_rasterize_forward_packed_ex(int img_h, int img_w, int tiles_x, int tiles_y, int m,
+                                               const int32_t *tile_bins, const int32_t *tile_order,
+                                               const int32_t *bin_stats, const float *background, void *records,
+                                               float *out_img, float *final_Ts, int32_t *final_idx,
+                                               unsigned flags, gsb_stream_t stream) {
+    return blend_forward(img_h, img_w, tiles_x, tiles_y, m, tile_bins, tile_order, bin_stats, background, records,
+                         out_img, final_Ts, final_idx, flags, stream);
 }
 
 // Diagnostic twin of gsb_rasterize_forward_packed: same outputs, plus pair_counts (device uint64[4], accumulated --
@@ -322,8 +355,8 @@ extern "C" int gsb_rasterize_forward_count(int img_h, int img_w, int tiles_x, in
         reinterpret_cast<char *>(records) + gsb_raster_records_bytes(m) - 256);
     GSB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
     const int num_tiles = tiles_x * tiles_y;
-    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel<true>, num_tiles);
-    rasterize_forward_kernel<true><<<grid, RK_THREADS, 0, s>>>(
+    const int grid = gsb_blend_grid((const void *)rasterize_forward_kernel<true, false>, num_tiles);
+    rasterize_forward_kernel<true, false><<<grid, RK_THREADS, 0, s>>>(
         img_h, img_w, tiles_x, num_tiles, reinterpret_cast<const int2 *>(tile_bins),
         reinterpret_cast<const GsbRecord *>(records), background, out_img, final_Ts, final_idx, counters, nullptr,
         pair_counts, nullptr);
@@ -348,7 +381,7 @@ int gsb_sm_count() {
 // costs a few microseconds of host time per call, so its result is cached per (thread, device, kernel).
 int gsb_blend_grid(const void *kernel, int num_tiles) {
     struct Entry { const void *kernel; int dev; int per_sm; };
-    static thread_local Entry cache[4] = {};
+    static thread_local Entry cache[8] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     int per_sm = 0;

@@ -131,11 +131,11 @@ class GaussianModel:
         fov_y = 2.0 * math.atan(height / (2.0 * fy))
         proj = projection_matrix(0.001, 1000.0, fov_x, fov_y, dev)
         cam_pos = T.reshape(3).to(dev)
-        scales, quats, opac, viewdirs = ops.ActivateGaussians.apply(self.means, self.scales, self.quats,
-                                                                    self.opacities, cam_pos)
         tb = ops.tile_bounds(width, height)
-        xys, depths, radii, conics, num_tiles_hit, _ = ops.ProjectGaussians.apply(
-            self.means, scales, 1.0, quats, view, proj @ view, fx, fy, cx, cy, height, width, tb)
+        # model.cpp:148-150,200 inside the projection: exp(scales), quaternion normalisation, sigmoid(opacities)
+        xys, depths, radii, conics, num_tiles_hit, _, opac = ops.ProjectGaussiansActivated.apply(
+            self.means, self.scales, 1.0, self.quats, self.opacities, view, proj @ view, fx, fy, cx, cy, height,
+            width, tb)
         self.xys, self.radii, self.numTilesHit = xys, radii, num_tiles_hit
         xys.retain_grad()
         if float(radii.sum()) == 0.0:
@@ -145,9 +145,9 @@ class GaussianModel:
         # + 0.5 and clamp_min fused (and their gradients written straight into the two feature tensors' grads)
         rgbs = ops.SphericalHarmonicsRgb.apply(degrees_to_use, self.means.detach(), cam_pos, self.featuresDc,
                                                self.featuresRest)
-        rgb = ops.RasterizeGaussians.apply(xys, depths, radii, conics, num_tiles_hit, rgbs, opac, height, width,
-                                           self.backgroundColor)
-        return torch.clamp_max(rgb, 1.0)
+        # model.cpp:213-222: rasterize + clamp_max(rgb, 1) in the blend kernel's epilogue
+        return ops.RasterizeGaussiansClamped.apply(xys, depths, radii, conics, num_tiles_hit, rgbs, opac, height,
+                                                   width, self.backgroundColor)
 
     def main_loss(self, rgb, gt, ssim_weight):
         """Model::mainLoss (model.cpp:780-784), fused forward + gradient."""

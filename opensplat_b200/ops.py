@@ -275,32 +275,42 @@ def bucket_sort_pack(n, m_capacity, len_capacity, depths, radii, cum_tiles_hit, 
     return records, idx, gs
 
 
+CLAMP_MAX_ONE = 1   # GSB_RASTER_CLAMP_MAX_ONE (include/gsplat_b200.h)
+
+
 def rasterize_forward_packed(tile_bounds_, img_size, m_capacity, tile_bins, records, background, stats=None,
-                             tile_order=None):
+                             tile_order=None, flags=0):
     W, H = img_size[0], img_size[1]
     out = _empty((H, W, 3), torch.float32, records)
     fT = _empty((H, W), torch.float32, records)
     fI = _empty((H, W), torch.int32, records)
     if tile_order is None:
         tile_order = getattr(tile_bins, "tile_order", None)
-    capi.check(capi.lib().gsb_rasterize_forward_packed(
+    capi.check(capi.lib().gsb_rasterize_forward_packed_ex(
         H, W, tile_bounds_[0], tile_bounds_[1], m_capacity, capi.ptr(tile_bins), capi.ptr(tile_order), capi.ptr(stats),
-        capi.ptr(capi.f32(background)), capi.ptr(records), capi.ptr(out), capi.ptr(fT), capi.ptr(fI),
+        capi.ptr(capi.f32(background)), capi.ptr(records), capi.ptr(out), capi.ptr(fT), capi.ptr(fI), int(flags),
         capi.stream()))
     return out, fT, fI
 
 
 def rasterize_forward(tile_bounds_, img_size, gaussian_ids_sorted, sorted_index, tile_bins, xys, conics,
-                      colors, opacities, background):
+                      colors, opacities, background, flags=0):
     W, H = img_size[0], img_size[1]
     m = gaussian_ids_sorted.shape[0]
     L = capi.lib()
     records = torch.empty(L.gsb_raster_records_bytes(m), dtype=torch.uint8, device=xys.device)
+    if colors.shape[-1] != 3:
+        raise ValueError("only 3-channel colors are supported")  # the N-D path is dead code in OpenSplat
+    if flags:
+        capi.check(L.gsb_pack_records(
+            m, capi.ptr(gaussian_ids_sorted), capi.ptr(sorted_index), capi.ptr(capi.f32(xys)),
+            capi.ptr(capi.f32(conics)), capi.ptr(capi.f32(colors)), capi.ptr(capi.f32(opacities)), capi.ptr(records),
+            capi.stream()))
+        return rasterize_forward_packed(tile_bounds_, img_size, m, tile_bins, records, background, None, None,
+                                        flags) + (records,)
     out = _empty((H, W, 3), torch.float32, xys)
     fT = _empty((H, W), torch.float32, xys)
     fI = _empty((H, W), torch.int32, xys)
-    if colors.shape[-1] != 3:
-        raise ValueError("only 3-channel colors are supported")  # the N-D path is dead code in OpenSplat
     capi.check(L.gsb_rasterize_forward(
         H, W, tile_bounds_[0], tile_bounds_[1], m, capi.ptr(gaussian_ids_sorted), capi.ptr(sorted_index),
         capi.ptr(tile_bins), capi.ptr(capi.f32(xys)), capi.ptr(capi.f32(conics)), capi.ptr(capi.f32(colors)),
@@ -310,7 +320,7 @@ def rasterize_forward(tile_bounds_, img_size, gaussian_ids_sorted, sorted_index,
 
 
 def rasterize_backward(img_height, img_width, n, m, tile_bins, conics, opacities, records, cum_tiles_hit,
-                       background, final_Ts, final_idx, v_output, v_output_alpha=None, tile_order=None):
+                       background, final_Ts, final_idx, v_output, v_output_alpha=None, tile_order=None, flags=0):
     L = capi.lib()
     tb = tile_bounds(img_width, img_height)
     rows = _ws.get(final_Ts.device, "grad_rows", L.gsb_raster_grad_rows_bytes(m) + 16)
@@ -320,13 +330,13 @@ def rasterize_backward(img_height, img_width, n, m, tile_bins, conics, opacities
     v_colors = _empty((n, 3), torch.float32, final_Ts)
     v_opacity = _empty((n, 1), torch.float32, final_Ts)
     v_output = capi.f32(v_output)
-    capi.check(L.gsb_rasterize_backward_ordered(
+    capi.check(L.gsb_rasterize_backward_ex(
         img_height, img_width, tb[0], tb[1], n, m, capi.ptr(tile_bins), capi.ptr(tile_order), capi.ptr(capi.f32(conics)),
         capi.ptr(capi.f32(opacities)), capi.ptr(records), capi.ptr(cum_tiles_hit),
         capi.ptr(capi.f32(background)), capi.ptr(final_Ts), capi.ptr(final_idx),
         capi.ptr(v_output), capi.ptr(v_output_alpha) if v_output_alpha is not None else None,
         rows.data_ptr() + off, capi.ptr(v_xy), capi.ptr(v_conic), capi.ptr(v_colors), capi.ptr(v_opacity),
-        capi.stream()))
+        int(flags), capi.stream()))
     return v_xy, v_conic, v_colors, v_opacity
 
 
@@ -363,6 +373,11 @@ class ProjectGaussians(torch.autograd.Function):
 class RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xys, depths, radii, conics, numTilesHit, colors, opacity, imgHeight, imgWidth, background):
+        return RasterizeGaussians._forward(ctx, 0, xys, depths, radii, conics, numTilesHit, colors, opacity,
+                                           imgHeight, imgWidth, background)
+
+    @staticmethod
+    def _forward(ctx, flags, xys, depths, radii, conics, numTilesHit, colors, opacity, imgHeight, imgWidth, background):
         numPoints = xys.shape[0]
         tb = tile_bounds(imgWidth, imgHeight)
         if colors.shape[-1] != 3:
@@ -379,13 +394,14 @@ class RasterizeGaussians(torch.autograd.Function):
             if m_cap > 0:
                 records, _, _ = bucket_sort_pack(numPoints, m_cap, len_cap, depths, radii, cum, tb, bins, stats, ws)
                 out, fT, fI = rasterize_forward_packed(tb, (imgWidth, imgHeight, 1), m_cap, bins, records,
-                                                       background, stats)
+                                                       background, stats, None, flags)
             numIntersects, max_len, overflow = plan.wait()
             if not overflow:
                 if m_cap == 0:   # no plan yet and nothing on screen: background only
                     records = torch.empty(capi.lib().gsb_raster_records_bytes(0), dtype=torch.uint8,
                                           device=xys.device)
-                    out, fT, fI = rasterize_forward_packed(tb, (imgWidth, imgHeight, 1), 0, bins, records, background)
+                    out, fT, fI = rasterize_forward_packed(tb, (imgWidth, imgHeight, 1), 0, bins, records, background,
+                                                           None, None, flags)
                 break
             if max_len <= limit:
                 plan.grow(numIntersects, max_len)
@@ -397,9 +413,9 @@ class RasterizeGaussians(torch.autograd.Function):
             _, _, _, gs, bins, idx = binAndSortGaussians(numPoints, m_cap, xys, depths, radii, cum, tb,
                                                          return_index=True)
             out, fT, fI, records = rasterize_forward(tb, (imgWidth, imgHeight, 1), gs, idx, bins, xys, conics,
-                                                     colors, opacity, background)
+                                                     colors, opacity, background, flags)
             break
-        ctx.meta = (int(imgHeight), int(imgWidth), numPoints, m_cap)
+        ctx.meta = (int(imgHeight), int(imgWidth), numPoints, m_cap, flags)
         order = getattr(bins, "tile_order", None)
         ctx.has_order = order is not None
         ctx.save_for_backward(bins, conics, opacity, records, cum, background, fT, fI,
@@ -408,13 +424,79 @@ class RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, v_outImg):
-        H, W, n, m = ctx.meta
+        H, W, n, m, flags = ctx.meta
         bins, conics, opacity, records, cum, background, fT, fI, order = ctx.saved_tensors
         v_xy, v_conic, v_colors, v_opacity = rasterize_backward(H, W, n, m, bins, conics, opacity, records, cum,
                                                                 background, fT, fI, v_outImg.contiguous(), None,
-                                                                tile_order=order if ctx.has_order else None)
+                                                                tile_order=order if ctx.has_order else None,
+                                                                flags=flags)
         # 10 slots; grads for xys(0), conics(3), colors(5), opacity(6) (rasterize_gaussians.cpp:129-139)
         return v_xy, None, None, v_conic, None, v_colors, v_opacity, None, None, None
+
+
+class RasterizeGaussiansClamped(RasterizeGaussians):
+    """`clamp_max(RasterizeGaussians(...), 1)` (model.cpp:213-222) as ONE operator: the blend kernel's epilogue writes
+    the clamped image and the backward kernel applies clamp_max's gradient mask (GSB_RASTER_CLAMP_MAX_ONE).  Same
+    arguments and gradient slots as RasterizeGaussians.  C++ twin: gsb::RasterizeGaussiansClamped."""
+
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, numTilesHit, colors, opacity, imgHeight, imgWidth, background):
+        return RasterizeGaussians._forward(ctx, CLAMP_MAX_ONE, xys, depths, radii, conics, numTilesHit, colors,
+                                           opacity, imgHeight, imgWidth, background)
+
+
+class ProjectGaussiansActivated(torch.autograd.Function):
+    """ProjectGaussians on the RAW parameters of the model (model.cpp:148-150,200 + 152-165 as one operator):
+    `scales` are log-scales (exp fused), `quats` un-normalised (the projection normalises), and the opacity logits
+    ride along: returns (xys, depths, radii, conics, numTilesHit, cov3d, opacities [N,1] = sigmoid(logits)).
+    Gradients come back w.r.t. the raw parameters.  C++ twin: gsb::ProjectGaussiansActivated."""
+
+    @staticmethod
+    def forward(ctx, means, logScales, globScale, rawQuats, opacityLogits, viewMat, projMat, fx, fy, cx, cy,
+                imgHeight, imgWidth, tileBounds, clipThresh=0.01):
+        n = means.shape[0]
+        m3, ls, rq = capi.f32(means), capi.f32(logScales), capi.f32(rawQuats)
+        ol = capi.f32(opacityLogits).reshape(n)
+        vm, pm = capi.f32(viewMat), capi.f32(projMat)
+        cov3d = _empty((n, 6), torch.float32, m3)
+        xys = _empty((n, 2), torch.float32, m3)
+        depths = _empty((n,), torch.float32, m3)
+        radii = _empty((n,), torch.int32, m3)
+        conics = _empty((n, 3), torch.float32, m3)
+        nth = _empty((n,), torch.int32, m3)
+        opac = _empty((n, 1), torch.float32, m3)
+        capi.check(capi.lib().gsb_project_forward_activated(
+            n, capi.ptr(m3), capi.ptr(ls), float(globScale), capi.ptr(rq), capi.ptr(ol), capi.ptr(vm), capi.ptr(pm),
+            float(fx), float(fy), float(cx), float(cy), int(imgHeight), int(imgWidth), tileBounds[0], tileBounds[1],
+            float(clipThresh), capi.ptr(cov3d), capi.ptr(xys), capi.ptr(depths), capi.ptr(radii), capi.ptr(conics),
+            capi.ptr(nth), capi.ptr(opac), capi.stream()))
+        ctx.meta = (float(globScale), float(fx), float(fy), int(imgHeight), int(imgWidth), tuple(opacityLogits.shape))
+        ctx.save_for_backward(m3, ls, rq, vm, pm, radii, conics, opac)
+        ctx.mark_non_differentiable(radii, nth)
+        return xys, depths, radii, conics, nth, cov3d, opac
+
+    @staticmethod
+    def backward(ctx, v_xys, v_depths, v_radii, v_conics, v_numTiles, v_cov3d, v_opac):
+        m3, ls, rq, vm, pm, radii, conics, opac = ctx.saved_tensors
+        gs, fx, fy, H, W, ol_shape = ctx.meta
+        n = m3.shape[0]
+        if v_xys is None:
+            v_xys = torch.zeros_like(m3[:, :2])
+        if v_conics is None:
+            v_conics = torch.zeros_like(conics)
+        v_mean = _empty((n, 3), torch.float32, m3)
+        v_ls = _empty((n, 3), torch.float32, m3)
+        v_rq = _empty((n, 4), torch.float32, m3)
+        v_ol = _empty((n,), torch.float32, m3)
+        vx, vc = capi.f32(v_xys), capi.f32(v_conics)
+        vd = capi.f32(v_depths) if v_depths is not None else None
+        vo = capi.f32(v_opac).reshape(n) if v_opac is not None else None
+        capi.check(capi.lib().gsb_project_backward_activated(
+            n, capi.ptr(m3), capi.ptr(ls), gs, capi.ptr(rq), capi.ptr(opac), capi.ptr(vm), capi.ptr(pm), fx, fy, H, W,
+            capi.ptr(radii), capi.ptr(conics), capi.ptr(vx), capi.ptr(vd), capi.ptr(vc), capi.ptr(vo),
+            capi.ptr(v_mean), capi.ptr(v_ls), capi.ptr(v_rq), capi.ptr(v_ol), capi.stream()))
+        # 15 slots; grads for means(0), logScales(1), rawQuats(3), opacityLogits(4)
+        return (v_mean, v_ls, None, v_rq, v_ol.reshape(ol_shape)) + (None,) * 10
 
 
 class SphericalHarmonics(torch.autograd.Function):

@@ -9,6 +9,9 @@
 //   save          -> Model::save        (model.cpp:496-594; .ply or .splat by extension)
 //   train         -> the body of the reference's training loop (opensplat.cpp:151-170) for a few steps
 //   load          -> Model::loadPly     (model.cpp:614-778)
+//   train_fused   -> (build (2) only) the same loop with the opt-in one-liners of csrc/ops/fused_extras.hpp in place of
+//                    the bodies of Model::forward and Model::mainLoss; everything else (optimizers, schedulers,
+//                    afterTrain) is still the reference's code
 // Nothing of the reference is copied: a Model is constructed through its own constructor (with a stub for the
 // nanoflann-based PointsTensor::scales(), whose result we overwrite anyway), its public tensors are replaced by the
 // caller's, its optimizers are re-created by its own setupOptimizers(), and the Adam moments are injected as the
@@ -17,6 +20,9 @@
 #include <torch/library.h>
 
 #include "model.hpp"
+#ifdef GSB_DRIVER_FUSED
+#include "fused_extras.hpp"   // the opt-in fused operators of the B200 operator layer (csrc/ops)
+#endif
 
 // ---- symbols of reference translation units we do not link (never reached by the calls above) ----
 torch::Tensor PointsTensor::scales() { return torch::ones({tensor.size(0), 1}, torch::kFloat32); }
@@ -127,11 +133,12 @@ void save(std::vector<Tensor> params, std::string filename, int64_t step, bool k
 // The body of the reference's training loop (opensplat.cpp:151-170) for steps first_step .. first_step+num_steps-1,
 // cameras taken round-robin: zero_grad -> Model::forward -> Model::mainLoss -> backward -> optimizersStep ->
 // schedulersStep -> afterTrain.  Returns {losses [S], gaussian counts [S], last rendered image, params(6)}.
-std::vector<Tensor> train(std::vector<Tensor> params, Tensor camToWorlds, Tensor gts, double fx, double fy, double cx,
-                          double cy, int64_t height, int64_t width, int64_t first_step, int64_t num_steps,
-                          double ssimWeight, int64_t seed, int64_t shDegreeInterval, int64_t numCameras,
-                          int64_t refineEvery, int64_t warmupLength, int64_t resetAlphaEvery, double densifyGradThresh,
-                          double densifySizeThresh, int64_t stopScreenSizeAt, double splitScreenSize, int64_t maxSteps) {
+std::vector<Tensor> train_impl(bool fused, std::vector<Tensor> params, Tensor camToWorlds, Tensor gts, double fx,
+                               double fy, double cx, double cy, int64_t height, int64_t width, int64_t first_step,
+                               int64_t num_steps, double ssimWeight, int64_t seed, int64_t shDegreeInterval,
+                               int64_t numCameras, int64_t refineEvery, int64_t warmupLength, int64_t resetAlphaEvery,
+                               double densifyGradThresh, double densifySizeThresh, int64_t stopScreenSizeAt,
+                               double splitScreenSize, int64_t maxSteps) {
     auto m = make_model(params, numCameras, refineEvery, warmupLength, resetAlphaEvery, densifyGradThresh,
                         densifySizeThresh, stopScreenSizeAt, splitScreenSize, maxSteps, false, 1.0,
                         torch::zeros({3}, torch::kFloat32), shDegreeInterval);
@@ -148,9 +155,30 @@ std::vector<Tensor> train(std::vector<Tensor> params, Tensor camToWorlds, Tensor
     for (int64_t step = first_step; step < first_step + num_steps; ++step) {
         const int64_t v = (step - 1) % V;
         m->optimizersZeroGrad();
-        rgb = m->forward(cams[v], (int)step);
         Tensor gt = gts[v].to(device);
-        Tensor loss = m->mainLoss(rgb, gt, (float)ssimWeight);
+        Tensor loss;
+#ifdef GSB_DRIVER_FUSED
+        if (fused) {
+            // what the bodies of Model::forward / Model::mainLoss become when a maintainer opts in
+            Camera &cam = cams[v];
+            const float sf = (float)m->getDownscaleFactor((int)step);
+            const int h = static_cast<int>(static_cast<float>(cam.height) / sf);
+            const int w = static_cast<int>(static_cast<float>(cam.width) / sf);
+            auto r = gsb::modelForward(m->means, m->scales, m->quats, m->featuresDc, m->featuresRest, m->opacities,
+                                       m->backgroundColor, cam.camToWorld, cam.fx / sf, cam.fy / sf, cam.cx / sf,
+                                       cam.cy / sf, h, w, (std::min<int>)((int)step / m->shDegreeInterval, m->shDegree));
+            m->xys = r.xys;
+            m->radii = r.radii;
+            m->lastHeight = h;
+            m->lastWidth = w;
+            rgb = r.rgb;
+            loss = gsb::MainLoss::apply(rgb, gt, ssimWeight);
+        } else
+#endif
+        {
+            rgb = m->forward(cams[v], (int)step);
+            loss = m->mainLoss(rgb, gt, (float)ssimWeight);
+        }
         loss.backward();
         losses.push_back(loss.item<float>());
         m->optimizersStep();
@@ -164,6 +192,29 @@ std::vector<Tensor> train(std::vector<Tensor> params, Tensor camToWorlds, Tensor
                                m->featuresRest.detach().clone(), m->opacities.detach().clone()};
     return out;
 }
+
+std::vector<Tensor> train(std::vector<Tensor> params, Tensor camToWorlds, Tensor gts, double fx, double fy, double cx,
+                          double cy, int64_t height, int64_t width, int64_t first_step, int64_t num_steps,
+                          double ssimWeight, int64_t seed, int64_t shDegreeInterval, int64_t numCameras,
+                          int64_t refineEvery, int64_t warmupLength, int64_t resetAlphaEvery, double densifyGradThresh,
+                          double densifySizeThresh, int64_t stopScreenSizeAt, double splitScreenSize, int64_t maxSteps) {
+    return train_impl(false, params, camToWorlds, gts, fx, fy, cx, cy, height, width, first_step, num_steps, ssimWeight,
+                      seed, shDegreeInterval, numCameras, refineEvery, warmupLength, resetAlphaEvery, densifyGradThresh,
+                      densifySizeThresh, stopScreenSizeAt, splitScreenSize, maxSteps);
+}
+
+#ifdef GSB_DRIVER_FUSED
+std::vector<Tensor> train_fused(std::vector<Tensor> params, Tensor camToWorlds, Tensor gts, double fx, double fy,
+                                double cx, double cy, int64_t height, int64_t width, int64_t first_step,
+                                int64_t num_steps, double ssimWeight, int64_t seed, int64_t shDegreeInterval,
+                                int64_t numCameras, int64_t refineEvery, int64_t warmupLength, int64_t resetAlphaEvery,
+                                double densifyGradThresh, double densifySizeThresh, int64_t stopScreenSizeAt,
+                                double splitScreenSize, int64_t maxSteps) {
+    return train_impl(true, params, camToWorlds, gts, fx, fy, cx, cy, height, width, first_step, num_steps, ssimWeight,
+                      seed, shDegreeInterval, numCameras, refineEvery, warmupLength, resetAlphaEvery, densifyGradThresh,
+                      densifySizeThresh, stopScreenSizeAt, splitScreenSize, maxSteps);
+}
+#endif
 
 // Model::loadPly (model.cpp:614-778) -> {step (int64 scalar), means, scales, quats, featuresDc, featuresRest, opacities}
 std::vector<Tensor> load(std::string filename, bool keepCrs, double scale, Tensor translation, Tensor like) {
@@ -187,5 +238,8 @@ TORCH_LIBRARY(GSB_DRIVER_LIB, m) {
     m.def("after_train", &after_train);
     m.def("save", &save);
     m.def("train", &train);
+#ifdef GSB_DRIVER_FUSED
+    m.def("train_fused", &train_fused);
+#endif
     m.def("load", &load);
 }

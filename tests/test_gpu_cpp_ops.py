@@ -206,3 +206,131 @@ def test_cpp_fused_activation_and_colour_operators_match_python_mirrors():
     ref = torch.clamp_min(co.spherical_harmonics(2, vd, torch.cat([dc[:, None, :], rest], 1).detach()) + 0.5, 0.0)
     assert float((a[4] - ref).abs().max()) <= 3e-6
     assert float((a[0] - torch.exp(ls.detach())).abs().max()) <= 2e-6 * float(torch.exp(ls.detach()).max())
+
+
+def _raw_model_scene(n, W, H, seed):
+    """A make_scene scene expressed in the model's RAW parameters (log-scales, un-normalised quaternions, opacity
+    logits) plus bright colours, so that the activations and the clamp all have something to do."""
+    from opensplat_b200.scene import make_scene
+    sc = make_scene(n, W, H, scale=0.25, sh_degree=0, opacity=(0.05, 0.9), seed=seed)
+    rng = np.random.default_rng(seed)
+    raw = {
+        "means": torch.from_numpy(sc["means"]).to(DEV),
+        "ls": torch.from_numpy(np.log(sc["scales"])).to(DEV),
+        "rq": torch.from_numpy(sc["quats"] * rng.uniform(0.5, 2.0, (n, 1)).astype(np.float32)).to(DEV),
+        "ol": torch.from_numpy(np.log(sc["opacities"] / (1 - sc["opacities"])).astype(np.float32)).reshape(n, 1).to(DEV),
+        "colors": torch.from_numpy(rng.uniform(0.0, 1.6, (n, 3)).astype(np.float32)).to(DEV),
+    }
+    cam = dict(view=torch.from_numpy(sc["viewmat"]).to(DEV), proj=torch.from_numpy(sc["projmat"]).to(DEV),
+               fx=sc["fx"], fy=sc["fy"], cx=sc["cx"], cy=sc["cy"])
+    return raw, cam
+
+
+@pytest.mark.parametrize("n,W,H", [(20_000, 320, 208), (1, 33, 17)])
+def test_fused_projection_and_clamped_rasterizer_match_the_unfused_sequence(n, W, H):
+    """SURVEY 8f row 1, the last glue ops of Model::forward: exp / normalize / sigmoid folded into the projection
+    (ProjectGaussiansActivated) and clamp_max(rgb, 1) folded into the blend kernels (RasterizeGaussiansClamped),
+    against the sequence model.cpp:148-150,152-165,200,213-222 runs -- torch activations + ProjectGaussians +
+    RasterizeGaussians + torch.clamp_max -- with torch autograd through it.  The clamped rasterizer has the same
+    arithmetic as the plain one, so image and gradients must be BIT-identical; the projection differs by rounding
+    only (one quaternion normalisation instead of two, expf inside the no-FMA translation unit)."""
+    raw, cam = _raw_model_scene(n, W, H, seed=n + 5)
+    tb = ops.tile_bounds(W, H)
+    bg = torch.tensor([1.0, 0.4, 0.9], device=DEV)
+    w_img = torch.randn(H, W, 3, device=DEV)
+    leaves = [raw[k].clone().requires_grad_() for k in ("means", "ls", "rq", "ol", "colors")]
+
+    def unfused(means, ls, rq, ol, colors):
+        scales, quats, opac = torch.exp(ls), rq / rq.norm(dim=-1, keepdim=True), torch.sigmoid(ol)
+        xys, depths, radii, conics, nth, _ = ops.ProjectGaussians.apply(
+            means, scales, 1.0, quats, cam["view"], cam["proj"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, tb)
+        rgb = ops.RasterizeGaussians.apply(xys, depths, radii, conics, nth, colors, opac, H, W, bg)
+        return torch.clamp_max(rgb, 1.0), (xys, depths, radii, conics, nth, opac), rgb
+
+    def fused(means, ls, rq, ol, colors):
+        xys, depths, radii, conics, nth, _, opac = ops.ProjectGaussiansActivated.apply(
+            means, ls, 1.0, rq, ol, cam["view"], cam["proj"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, tb)
+        rgb = ops.RasterizeGaussiansClamped.apply(xys, depths, radii, conics, nth, colors, opac, H, W, bg)
+        return rgb, (xys, depths, radii, conics, nth, opac), None
+
+    def grads(fn):
+        for t in leaves:
+            t.grad = None
+        img, proj_out, raw_img = fn(*leaves)
+        (img * w_img).sum().backward()
+        return img.detach(), proj_out, [t.grad.clone() for t in leaves], raw_img
+
+    img_u, pu, gu, raw_img = grads(unfused)
+    img_f, pf, gf, _ = grads(fused)
+    # --- projection: same integers (a radius could flip by rounding; none may in more than 0.1 % of the Gaussians)
+    same = (pu[2] == pf[2]) & (pu[4] == pf[4])
+    assert float(same.float().mean()) >= 0.999
+    for a, b, tol in ((pu[0], pf[0], 0.0), (pu[1], pf[1], 0.0), (pu[3], pf[3], 1e-4), (pu[5], pf[5], 1e-6)):   # xys, depths: means only
+        d = (a - b).abs()[same] if a.shape[0] == same.shape[0] else (a - b).abs()
+        assert float(d.max()) <= tol * max(1.0, float(b.abs().max())), float(d.max())
+    # --- the clamp really cut something, image within rounding of the unfused one, gradients too
+    if n > 1:
+        assert float((raw_img > 1.0).float().mean()) > 0.02
+    assert float(img_f.max()) <= 1.0
+    assert float((img_u - img_f).abs().max()) <= 2e-4
+    for a, b in zip(gu, gf):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= 2e-3, rel_l2(a.cpu().numpy(), b.cpu().numpy())
+
+    # --- the clamped rasterizer alone, on identical inputs: bit-identical image and gradients
+    xys, depths, radii, conics, nth, opac = [t.detach() for t in pf]
+    outs = []
+    for op, clamp_after in ((ops.RasterizeGaussians, True), (ops.RasterizeGaussiansClamped, False)):
+        xl, cl, col, ol_ = (t.clone().requires_grad_() for t in (xys, conics, raw["colors"], opac))
+        img = op.apply(xl, depths, radii, cl, nth, col, ol_, H, W, bg)
+        if clamp_after:
+            img = torch.clamp_max(img, 1.0)
+        (img * w_img).sum().backward()
+        outs.append([img.detach(), xl.grad, cl.grad, col.grad, ol_.grad])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+    # --- C++ twins (gsb::ProjectGaussiansActivated / gsb::RasterizeGaussiansClamped): same kernels, same bits
+    co = cpp_ops.ops()
+
+    def fused_cpp(means, ls, rq, ol, colors):
+        xys, depths, radii, conics, nth, _, opac = co.project_gaussians_activated(
+            means, ls, 1.0, rq, ol, cam["view"], cam["proj"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, 0.01)
+        rgb = co.rasterize_gaussians_clamped(xys, depths, radii, conics, nth, colors, opac, H, W, bg)
+        return rgb, (xys, depths, radii, conics, nth, opac), None
+
+    img_c, pc, gc, _ = grads(fused_cpp)
+    assert torch.equal(img_c, img_f)
+    for a, b in zip(pc, pf):
+        assert torch.equal(a, b)
+    for a, b in zip(gc, gf):
+        assert torch.equal(a, b)
+
+
+def test_clamped_rasterizer_on_the_generic_fallback_path():
+    """Tile lists longer than the in-shared-memory sort takes (the operator falls back to the generic global sort and
+    gsb_pack_records): the clamp flag must travel down that branch as well."""
+    from opensplat_b200.scene import make_scene
+    n, W, H = 24_000, 64, 48
+    sc = make_scene(n, W, H, scale=0.5, sh_degree=0, opacity=(0.0045, 0.01), seed=n)
+    sc["means"][:, 0] = 0.25 + sc["means"][:, 0] * 0.05
+    sc["means"][:, 1] = sc["means"][:, 1] * 0.05
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    tb = ops.tile_bounds(W, H)
+    _, xys, depths, radii, conics, nth = ops.project_gaussians_forward(
+        t(sc["means"]), t(sc["scales"]), 1.0, t(sc["quats"]), t(sc["viewmat"]), t(sc["projmat"]), sc["fx"], sc["fy"],
+        sc["cx"], sc["cy"], H, W, tb)
+    colors = torch.from_numpy(np.random.default_rng(2).uniform(0.5, 3.0, (n, 3)).astype(np.float32)).to(DEV)
+    opac, bg = t(sc["opacities"]), torch.tensor([0.2, 0.9, 0.5], device=DEV)
+    w_img = torch.randn(H, W, 3, device=DEV)
+    outs = []
+    for op, clamp_after in ((ops.RasterizeGaussians, True), (ops.RasterizeGaussiansClamped, False)):
+        col, ol_ = colors.clone().requires_grad_(), opac.clone().requires_grad_()
+        img = op.apply(xys, depths, radii, conics, nth, col, ol_, H, W, bg)
+        if clamp_after:
+            raw_img = img.detach()
+            img = torch.clamp_max(img, 1.0)
+        (img * w_img).sum().backward()
+        outs.append([img.detach(), col.grad, ol_.grad])
+    assert float((raw_img > 1.0).float().mean()) > 0.001
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

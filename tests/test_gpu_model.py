@@ -95,6 +95,41 @@ def test_reference_model_cpp_unchanged_trains_on_b200_backend_and_mirror_follows
         assert float((rgb.detach() - ref_rgb).abs().max()) <= 2e-2
 
 
+@pytest.mark.skipif(not os.path.exists(LIB), reason="libopensplat_model_b200.so not built (needs /root/reference at build time)")
+def test_reference_training_loop_with_cpp_fused_opt_ins_follows_the_unchanged_one():
+    """SURVEY 8f row 1 from C++: the reference's loop with the bodies of Model::forward / Model::mainLoss swapped for
+    gsb::modelForward (ProjectGaussiansActivated -> SphericalHarmonicsRgb -> RasterizeGaussiansClamped) and
+    gsb::MainLoss (csrc/ops/fused_extras.hpp; driver op train_fused) against the UNCHANGED model.cpp on the same
+    operators: same losses to rounding, same refinement decisions; optimizers / schedulers / afterTrain are the
+    reference's own code in both runs."""
+    from opensplat_b200 import cpp_ops
+    cpp_ops.ops()
+    from opensplat_b200.densify import RefineConfig
+    torch.ops.load_library(LIB)
+    p, c2w, gts, (fx, fy, cx, cy), H, W = make_problem()
+    steps, seed, ssim_w, sh_int = 34, 11, 0.2, 8
+    cfg = RefineConfig(refine_every=10, warmup_length=15, reset_alpha_every=30, densify_grad_thresh=2e-5,
+                       densify_size_thresh=0.05, stop_screen_size_at=4000, split_screen_size=0.05, max_steps=200,
+                       num_cameras=3)
+    outs = []
+    for op in (torch.ops.opensplat_b200_model.train, torch.ops.opensplat_b200_model.train_fused):
+        params = [torch.from_numpy(p[x]).to(DEV) for x in PARAM_NAMES]
+        out = op(params, torch.from_numpy(c2w), torch.from_numpy(gts), fx, fy, cx, cy, H, W, 1, steps, ssim_w, seed,
+                 sh_int, cfg.num_cameras, cfg.refine_every, cfg.warmup_length, cfg.reset_alpha_every,
+                 cfg.densify_grad_thresh, cfg.densify_size_thresh, cfg.stop_screen_size_at, cfg.split_screen_size,
+                 cfg.max_steps)
+        outs.append((out[0].numpy(), out[1].numpy(), out[2], dict(zip(PARAM_NAMES, out[3:9]))))
+    (ref_loss, ref_cnt, ref_rgb, ref_p), (loss, cnt, rgb, par) = outs
+    assert ref_cnt[19] != ref_cnt[18] and ref_cnt[29] != ref_cnt[28]                # two refinements happened
+    assert np.abs(loss[:20] - ref_loss[:20]).max() <= 5e-5, np.abs(loss[:20] - ref_loss[:20]).max()
+    assert np.abs(cnt - ref_cnt).max() <= 0.02 * ref_cnt.max(), (cnt[[19, 29]], ref_cnt[[19, 29]])
+    assert np.abs(loss - ref_loss).max() <= 5e-3, np.abs(loss - ref_loss).max()
+    if np.array_equal(cnt, ref_cnt):
+        for k in PARAM_NAMES:
+            assert float((par[k] - ref_p[k]).abs().max()) <= 2e-3 * (1.0 + float(ref_p[k].abs().max())), k
+        assert float((rgb - ref_rgb).abs().max()) <= 2e-2
+
+
 def test_gaussian_model_save_matches_reference_writer(tmp_path):
     """GaussianModel.save == Model::save bytes (golden from the reference's own writer)."""
     from opensplat_b200.model import GaussianModel

@@ -5,7 +5,9 @@ mainLoss, backward, optimizersStep, schedulersStep, afterTrain statistics) on on
   a) the reference's model.cpp, UNCHANGED, over the gsplat_b200 operators (libopensplat_model_b200.so): the three
      operators are ours, everything around them is the reference's ATen glue (cat, exp, normalize, sigmoid, 5 grouped
      conv2d for SSIM + autograd, six torch::optim::Adam, index_put statistics);
-  b) opensplat_b200.model.GaussianModel: same loop with that glue fused.
+  b) the same C++ loop with gsb::modelForward / gsb::MainLoss (csrc/ops/fused_extras.hpp) opted in for the bodies
+     of Model::forward / Model::mainLoss -- optimizers, schedulers and afterTrain still the reference's code;
+  c) opensplat_b200.model.GaussianModel: same loop with all of that glue fused.
 
     python tools/bench_model_train.py [--n 1000000] [--steps 30]"""
 import argparse
@@ -65,11 +67,12 @@ def main():
     out["M"] = int(probe.numTilesHit.sum())
     del probe
 
-    def run_cpp(first, steps):
+    def run_cpp(first, steps, op=None):
+        op = op or torch.ops.opensplat_b200_model.train
         params = [torch.from_numpy(p[x]).to(dev) for x in PARAM_NAMES]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        r = torch.ops.opensplat_b200_model.train(
+        r = op(
             params, torch.from_numpy(c2w), gts, fx, fy, cx, cy, H, W, first, steps, 0.2, 1, 1000, 1, cfg.refine_every,
             cfg.warmup_length, cfg.reset_alpha_every, cfg.densify_grad_thresh, cfg.densify_size_thresh,
             cfg.stop_screen_size_at, cfg.split_screen_size, cfg.max_steps)
@@ -81,6 +84,16 @@ def main():
     dt = (t_big - t_small) / a.steps                     # subtract model construction + parameter upload
     out["reference_model_cpp_on_b200_ops"] = {"iters_per_s": 1.0 / dt, "ms_per_iter": dt * 1e3,
                                                "final_loss": float(r[0][-1])}
+
+    # the same C++ loop with the opt-in one-liners of csrc/ops/fused_extras.hpp for the bodies of Model::forward /
+    # Model::mainLoss (gsb::modelForward, gsb::MainLoss); optimizers, schedulers and afterTrain stay the reference's
+    fused_op = torch.ops.opensplat_b200_model.train_fused
+    run_cpp(3001, 3, fused_op)
+    t_small, _ = run_cpp(3001, 2, fused_op)
+    t_big, r = run_cpp(3001, 2 + a.steps, fused_op)
+    dt = (t_big - t_small) / a.steps
+    out["reference_loop_with_cpp_fused_opt_ins"] = {"iters_per_s": 1.0 / dt, "ms_per_iter": dt * 1e3,
+                                                     "final_loss": float(r[0][-1])}
 
     model = GaussianModel({k: torch.from_numpy(v) for k, v in p.items()}, cfg, device=dev)
     cam = Camera(W, H, fx, fy, cx, cy, c2w[0])

@@ -48,7 +48,7 @@ def build(force=False):
              f"-I{T}/include/torch/csrc/api/include", "-I/usr/local/cuda/include", f"-I{REF}"]
     srcs = [(os.path.join(tmp, "model.cpp"), []), (os.path.join(REF, "tensor_math.cpp"), []),
             (os.path.join(REF, "optim_scheduler.cpp"), []), (os.path.join(REF, "ssim.cpp"), []),
-            (driver, ["-DGSB_DRIVER_LIB=opensplat_b200_model"])]
+            (driver, ["-DGSB_DRIVER_LIB=opensplat_b200_model", "-DGSB_DRIVER_FUSED"])]
     cxx = os.environ.get("CXX", "g++")
 
     def cc(item):
