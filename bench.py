@@ -405,7 +405,8 @@ def run_ours(args):
 
     # H2D of every step's inputs (target image + camera) from pinned memory runs on a copy stream, one step
     # ahead of the compute (double buffer); the step's result (the loss) is copied D2H every step into one of two
-    # pinned slots and consumed one step later, so neither direction stalls the GPU.  All inside the timed region.
+    # pinned slots and consumed on the host two steps later (when its slot comes round again), so neither direction
+    # stalls the GPU or drains the launch queue.  All inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
     slots = [dict(tgt=torch.empty_like(pipe.target), vm=torch.empty_like(pipe.viewmat),
                   pm=torch.empty_like(pipe.projmat), ev=torch.cuda.Event(), used=torch.cuda.Event(),
@@ -427,9 +428,9 @@ def run_ours(args):
     def step_e2e():
         i = state["i"]
         cur, nxt = slots[i % 2], slots[(i + 1) % 2]
-        if i > 0:                                                # the PREVIOUS step's result, read on the host
-            nxt["loss_ev"].synchronize()
-            state["last_loss"] = float(nxt["loss"][0])
+        if i > 1:                                                # the result of step i-2 (this slot's previous use),
+            cur["loss_ev"].synchronize()                         # read on the host before the slot is written again:
+            state["last_loss"] = float(cur["loss"][0])           # the host never waits for the step still in flight
         prefetch(nxt)                                            # next step's inputs, overlapped
         state["i"] = i + 1
         torch.cuda.current_stream().wait_event(cur["ev"])       # this step's H2D has landed
