@@ -254,18 +254,23 @@ def _roofline(pipe, stage_ms, ms_step, workload, pairs):
 def _side_config(workload, dev, steps=5, warmup=3):
     """One-shot sub-record for another BASELINE config (C3 / C5) on this GPU: value, stages, roofline."""
     import torch
-    pipe, sc, cam, tgt = _setup_pipe(workload, dev, 0, 1, stage_timing=True)
+    pipe, sc, cam, tgt = _setup_pipe(workload, dev, 0, 1, stage_timing=False)
     for _ in range(warmup):
         pipe.forward_backward()
+
+    def region():
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            pipe.forward_backward()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    ms = region()                       # value: no instrumentation between the kernels
+    pipe.stage_timing = True            # stage times / roofline: the same steps with per-stage events
     pipe.stage_ms.clear(); pipe._steps_ev = []
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        pipe.forward_backward()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    ms_instr = region()
     stage_ms = pipe.resolve_stage_times()
     pairs = _pair_counts(pipe)
     roof, roof_path = _roofline(pipe, stage_ms, ms, workload, pairs)
@@ -274,7 +279,8 @@ def _side_config(workload, dev, steps=5, warmup=3):
            "gaussians": n, "width": W, "height": H, "intersections_binned": pipe.m,
            "intersections_reference": int(pipe.nth.sum()), "longest_tile_list": pipe.max_len,
            "tile_occupancy": pipe.tile_occupancy(),
-           "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "roofline": roof, "roofline_path": roof_path}
+           "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "ms_per_step_instrumented": ms_instr,
+           "roofline": roof, "roofline_path": roof_path}
     del pipe
     torch.cuda.empty_cache()
     return rec
@@ -356,11 +362,18 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_fwd_bwd()
-    pipe.stage_ms.clear(); pipe._steps_ev = []
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # the headline region: K steps, no instrumentation between the kernels
+    pipe.stage_timing = False
     ms_total = timed(step_fwd_bwd, args.steps)
+    # the same K steps again with a CUDA event at every stage boundary (stage times, roofline): the ~20 timing events
+    # per step cost 1-2 % (each one drains the launch pipeline for a moment), which is why they are not in the
+    # headline region; `ms_per_step_instrumented` says what the step took with them
+    pipe.stage_timing = True
+    pipe.stage_ms.clear(); pipe._steps_ev = []
+    ms_instr = timed(step_fwd_bwd, args.steps) / args.steps
     stage_ms = pipe.resolve_stage_times()
     m_timed = pipe.m
     ms_step = ms_total / args.steps
@@ -541,6 +554,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof, "roofline_path": roof_path,
         "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+        "ms_per_step_instrumented": ms_instr,
         "per_rank": per_rank,
         "tile_occupancy": occupancy,
         "exchange_check": exchange_check,
