@@ -73,14 +73,21 @@ def test_refine_schedule_matches_reference_defaults():
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    """The last bench line measured on the B200 (profiles/r01_bench_final.json) carries every key of the bench
+    """The last bench line measured on the B200 (profiles/r02_bench_final.json) carries every key of the bench
     contract; guards bench.py's output format against accidental regressions between GPU runs."""
     import json
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    lines = [json.loads(l) for l in open(os.path.join(root, "profiles", "r01_bench_final.json")) if l.startswith("{")]
+    lines = [json.loads(l) for l in open(os.path.join(root, "profiles", "r02_bench_final.json")) if l.startswith("{")]
     assert len(lines) == 1
     d = lines[0]
+    # round 2: pixel-pair throughput beside the HBM fraction, C3 / C5 sub-records, per-rank work, tile occupancy
+    p = d["roofline"]["pairs"]
+    assert p["pairs_blended"] > 0 and p["bwd_blended_pairs_per_s"] > 0 and p["fwd_evaluated_pairs_per_s"] > 0
+    assert set(d["other_configs"]) == {"c3_3M_4k_sh3", "c5_5M_1440p_dense"}
+    assert all(v["value"] > 0 and v["roofline"]["frac"] > 0 for v in d["other_configs"].values())
+    assert d["per_rank"][0]["intersections_binned"] < d["per_rank"][0]["intersections_reference"]
+    assert d["ms_per_step_instrumented"] >= d["ms_per_step"] and d["tile_occupancy"]
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
