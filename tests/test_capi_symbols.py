@@ -69,3 +69,51 @@ def test_cxx_libraries_use_the_shared_libstdcxx():
         assert "_ZNSo9_M_insertIlEERSoT_" not in out, f"{lib} embeds a static copy of libstdc++ (ostream::_M_insert<long>)"
         checked += 1
     assert checked >= 1
+
+
+def _prototypes():
+    """{name: (return type, [parameter types])} parsed from include/gsplat_b200.h (comments stripped)."""
+    txt = open(os.path.join(ROOT, "include", "gsplat_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for ret, name, params in re.findall(r"\b(int|size_t|const char \*)\s*(gsb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        protos[name] = (ret, plist)
+    return protos
+
+
+def _ctype_of(decl):
+    """ctypes class of one C parameter declaration of the header."""
+    import ctypes as C
+    if "*" in decl:
+        return C.c_void_p
+    base = decl.rsplit(" ", 1)[0].replace("const ", "").strip()
+    return {"int": C.c_int, "int32_t": C.c_int, "float": C.c_float, "size_t": C.c_size_t, "long long": C.c_longlong,
+            "unsigned": C.c_uint, "unsigned int": C.c_uint, "gsb_stream_t": C.c_void_p}[base]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every binding in capi._SIGS has the arity and the scalar/pointer classes of its prototype in
+    include/gsplat_b200.h (an int bound as a float, or a dropped argument, would otherwise only show as garbage on
+    the GPU box)."""
+    import ctypes as C
+    protos = _prototypes()
+    assert len(protos) >= 50, len(protos)
+    sigs = dict(capi._SIGS)
+    sigs.update(capi._OPT_SIGS)
+    checked = 0
+    for name, (ret, plist) in protos.items():
+        assert name in sigs, name
+        restype, argtypes = sigs[name]
+        assert len(argtypes) == len(plist), (name, len(argtypes), len(plist), plist)
+        for i, (a, decl) in enumerate(zip(argtypes, plist)):
+            want = _ctype_of(decl)
+            if want is C.c_void_p:     # pointers and the stream handle: bound as void* (or a typed pointer)
+                assert a is C.c_void_p or issubclass(a, C._Pointer), (name, i, decl, a)
+            else:
+                assert a is want, (name, i, decl, a, want)
+        want_ret = {"int": C.c_int, "size_t": C.c_size_t, "const char *": C.c_char_p}[ret]
+        assert restype is want_ret, (name, restype, want_ret)
+        checked += 1
+    assert checked == len(protos)
